@@ -1,0 +1,133 @@
+/*
+ * libstx_b200 — C ABI of the B200-native (sm_100a) log-mel front end and cosine scorer.
+ *
+ * This header is the drop-in boundary for ONE hot path of
+ * yuriyvnv/speech_transcript_embeddings (reference = R/, third-party transformers = TF/):
+ *
+ *   raw 16 kHz float32 PCM -> input_features + attention mask     (R/processor.py:79-126,
+ *                                                                   R/training/trainer_unfreeze.py:855-866)
+ *   cosine similarity of L2-normalised audio/text embeddings       (R/processor.py:148-159,
+ *                                                                   R/inference.py:121, R/cv_inference.py:105)
+ *
+ * The reference has no FFI: the path sits behind a Python object protocol (the HuggingFace
+ * feature-extractor __call__ and AudioTextProcessor's methods).  The Python host in
+ * speech_transcript_embeddings_b200/ mirrors that protocol and binds these symbols with
+ * ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every `d_*` pointer is a DEVICE pointer, `h_*` a HOST pointer;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) unless the name ends in `_host`, which synchronises before returning;
+ *   - return 0 on success, <0 on argument errors (STX_E*), >0 = a cudaError_t;
+ *     stx_last_error() returns a thread-local message for the last non-zero return;
+ *   - the caller allocates outputs and workspaces (ownership stays with the caller's allocator).
+ */
+#ifndef STX_B200_H_
+#define STX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STX_ABI_VERSION 1
+
+#define STX_EINVAL   (-1)  /* bad argument                                  */
+#define STX_ENOSPACE (-2)  /* workspace too small                           */
+#define STX_EDEVICE  (-3)  /* not an sm_100 device / CUDA runtime unusable  */
+
+/* recipe K constants (SeamlessM4TFeatureExtractor, TF/models/seamless_m4t/feature_extraction_seamless_m4t.py:60-87) */
+#define STX_K_FRAME   400
+#define STX_K_HOP     160
+#define STX_K_NFFT    512
+#define STX_K_NMEL    80
+#define STX_K_STRIDE  2
+/* recipe W constants (WhisperFeatureExtractor, TF/models/whisper/feature_extraction_whisper.py:69-103) */
+#define STX_W_NFFT    400
+#define STX_W_HOP     160
+#define STX_W_NMEL    80
+
+int         stx_abi_version(void);
+const char* stx_last_error(void);
+
+/* Number of CUDA kernels this library has launched since load (all entry points); bench.py's
+ * `gpu_launches` is the difference of this counter across the timed region. */
+uint64_t    stx_kernel_launch_count(void);
+
+/* Copies a host-side float64 table used by the kernels, for inspection by tests.
+ *   "k_window"  [400]      Povey window                      (TF/audio_utils.py:593, 601-602)
+ *   "k_mel"     [257*80]   Kaldi mel filters, row-major      (TF/audio_utils.py:516-530)
+ *   "w_window"  [400]      periodic Hann                     (TF/models/whisper/...:141)
+ *   "w_mel"     [201*80]   Slaney mel filters, row-major     (TF/models/whisper/...:95-103)
+ * Returns the number of doubles written (<= cap), or STX_EINVAL. */
+int64_t     stx_get_table(const char* name, double* h_out, int64_t cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * Recipe K: Kaldi-style fbank + per-clip per-bin CMVN + pad + stride-2 stacking + mask.
+ * Replaces SeamlessM4TFeatureExtractor.__call__ (TF/models/seamless_m4t/
+ * feature_extraction_seamless_m4t.py:141-302) as called at R/processor.py:101-105 and
+ * R/training/trainer_unfreeze.py:856-860.
+ *
+ *   d_pcm      packed float32 PCM of all clips (NOT pre-scaled by 2^15)
+ *   d_offsets  [B] start sample of each clip inside d_pcm (int64); multiples of 4 recommended
+ *   d_lengths  [B] samples per clip (int32).  T_b = 1 + (len-400)/160 frames (0 if len < 400)
+ *   max_length host copy of max_b len (sizes the grid; no device->host sync is ever made)
+ *   d_peak     NULL, or [B] float32 divisors: sample = pcm / d_peak[b] in float32 before
+ *              anything else (the reference's peak-normalise, R/processor.py:91-92)
+ *   T_pad      EVEN number of raw frames per clip in the padded output (TF .pad with
+ *              pad_to_multiple_of=2); frames >= T_pad are used for statistics but not stored
+ *   normalize  1 = per-bin (x-mean)/sqrt(var_ddof1+1e-7) (…seamless_m4t.py:257-262); 0 = raw log-mel
+ *   d_out      [B, T_pad/2, 160] float32 : out[b, j, 0:80] = frame 2j, out[b, j, 80:160] = frame 2j+1,
+ *              rows past the clip filled with padding_value (…seamless_m4t.py:281-300)
+ *   d_mask     NULL or [B, T_pad/2] int32: 1 iff frame 2j+1 < T_b (…seamless_m4t.py:292-293)
+ *   d_ws       workspace of at least stx_fbank_k_workspace() bytes
+ * ------------------------------------------------------------------------------------------- */
+int stx_fbank_k_workspace(int B, int max_length, size_t* bytes);
+int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B,
+                int max_length, const float* d_peak, int T_pad, float padding_value, int normalize,
+                float* d_out, int32_t* d_mask, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Per-clip max(1, max|x|) -> d_peak[b] (float32): the divisor of R/processor.py:91-92
+ * (division only happens when max|x| > 1; dividing by exactly 1.0f is the identity). */
+int stx_peak_abs(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B,
+                 float* d_peak, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Recipe W: Whisper log-mel.  Replaces WhisperFeatureExtractor.__call__ +
+ * _torch_extract_fbank_features (TF/models/whisper/feature_extraction_whisper.py:135-164, 189-342).
+ *
+ *   n_samples  clip length after pad/truncate (480000 for the stock extractor); multiple of 160
+ *   d_peak     NULL, or [B] float32 divisors as in stx_fbank_k
+ *   d_out      [B, 80, n_samples/160] float32
+ *   d_mask     NULL or [B, n_samples/160] int32 (sample mask every 160th sample, :328-337)
+ *   d_ws       workspace of at least stx_logmel_w_workspace() bytes
+ * ------------------------------------------------------------------------------------------- */
+int stx_logmel_w_workspace(int B, int n_samples, size_t* bytes);
+int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B,
+                 int n_samples, const float* d_peak, float* d_out, int32_t* d_mask, void* d_ws,
+                 size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cosine scoring.  Replaces AudioTextProcessor.compute_similarity (R/processor.py:148-159) and
+ * the F.normalize + (a*b).sum(dim=1) idiom at R/model.py:326-327, R/inference.py:121,
+ * R/cv_inference.py:105, R/training/trainer_unfreeze.py:1073-1074.
+ *
+ *   stx_cosine_pairwise   s[i]    = <a_i/max(|a_i|,1e-12), b_i/max(|b_i|,1e-12)>          [N]
+ *   stx_cosine_nxm        S[i, j] = <a_i/max(|a_i|,1e-12), b_j/max(|b_j|,1e-12)>          [N, M] (ld = M)
+ * A is [N, D], B is [M, D], row-major float32.  always_normalize = 0 reproduces the reference's
+ * conditional (rows are re-normalised only if some row norm of that operand deviates from 1 by
+ * more than 1e-4, torch.allclose semantics); 1 normalises unconditionally.
+ * d_ws: at least stx_cosine_workspace() bytes.
+ * ------------------------------------------------------------------------------------------- */
+int stx_cosine_workspace(int N, int M, int D, size_t* bytes);
+int stx_cosine_pairwise(const float* d_a, const float* d_b, int N, int D, int always_normalize,
+                        float* d_s, void* d_ws, size_t ws_bytes, void* stream);
+int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int always_normalize,
+                   float* d_S, void* d_ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STX_B200_H_ */

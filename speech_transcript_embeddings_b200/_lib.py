@@ -1,0 +1,71 @@
+"""ctypes binding of libstx_b200.so (the C ABI declared in include/stx_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "libstx_b200.so"
+
+# symbol -> (restype, argtypes); lists every function include/stx_b200.h declares
+_SIGNATURES = {
+    "stx_abi_version": (C.c_int, []),
+    "stx_last_error": (C.c_char_p, []),
+    "stx_kernel_launch_count": (C.c_uint64, []),
+    "stx_get_table": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64]),
+    "stx_fbank_k_workspace": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "stx_fbank_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                              C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "stx_peak_abs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "stx_logmel_w_workspace": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "stx_logmel_w": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "stx_cosine_workspace": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "stx_cosine_pairwise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "stx_cosine_nxm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class StxError(RuntimeError):
+    """A libstx_b200 entry point returned non-zero, or the library is unusable."""
+
+
+def exported_symbols():
+    return tuple(_SIGNATURES)
+
+
+def load() -> C.CDLL:
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not LIB_PATH.exists():
+                raise StxError(
+                    f"{LIB_PATH} is missing: build it with `python -m speech_transcript_embeddings_b200.build` "
+                    "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+            lib = C.CDLL(str(LIB_PATH))
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)     # AttributeError if the .so lacks a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            if lib.stx_abi_version() != 1:
+                raise StxError(f"libstx_b200 ABI {lib.stx_abi_version()} != 1: rebuild the library")
+            _lib = lib
+        return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().stx_last_error().decode(errors="replace")
+        raise StxError(f"{what} failed (rc={rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().stx_kernel_launch_count())

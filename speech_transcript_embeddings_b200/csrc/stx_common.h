@@ -1,0 +1,48 @@
+// Shared host-side plumbing of libstx_b200: error reporting, launch counting, float64 tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/stx_b200.h"
+
+namespace stx {
+
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+extern std::atomic<uint64_t> g_launches;
+
+#define STX_CUDA(call)                                             \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return stx::cuda_fail(e__, #call); \
+    } while (0)
+
+// every kernel launch of the library goes through this macro so that the launch counter is exact
+#define STX_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        stx::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) return stx::cuda_fail(e__, "launch " #kernel);   \
+    } while (0)
+
+// ---- float64 host tables (regenerated here, not read from anywhere) -------------------------
+const std::vector<double>& k_window();   // [400]  Povey
+const std::vector<double>& k_mel();      // [257*80] Kaldi mel, row-major [bin][mel]
+const std::vector<double>& w_window();   // [400]  periodic Hann
+const std::vector<double>& w_mel();      // [201*80] Slaney mel, row-major [bin][mel]
+
+// Compressed rows of a [nbins, nmel] filterbank: for mel m the non-zero weights are the
+// contiguous bins [first[m], first[m]+count[m]) stored at weights[offset[m]...].
+struct MelCsr {
+    std::vector<int>   first, count, offset;
+    std::vector<float> weights;
+};
+MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double scale);
+
+int check_device();   // 0 if the current device is sm_100, else STX_EDEVICE
+
+}  // namespace stx

@@ -1,0 +1,175 @@
+"""Thin torch-tensor front of the C ABI (include/stx_b200.h).
+
+Every function takes CUDA tensors, allocates outputs/workspaces with torch (so ownership stays with
+torch's caching allocator) and launches on torch's current stream.  PyTorch is plumbing here: device
+memory and streams.  All arithmetic happens in libstx_b200.so; there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+K_FRAME, K_HOP, K_NMEL = 400, 160, 80
+W_HOP, W_NMEL = 160, 80
+
+
+def _require_cuda(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.StxError(f"{name} must be a CUDA tensor (libstx_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def k_num_frames(n: int) -> int:
+    """Frames of a clip of n samples, centre=False framing 400/160 (TF/audio_utils.py:778)."""
+    return 1 + (n - K_FRAME) // K_HOP if n >= K_FRAME else 0
+
+
+def get_table(name: str) -> np.ndarray:
+    lib = _lib.load()
+    sizes = {"k_window": 400, "k_mel": 257 * 80, "w_window": 400, "w_mel": 201 * 80}
+    out = np.empty(sizes[name], np.float64)
+    n = lib.stx_get_table(name.encode(), out.ctypes.data_as(C.c_void_p), out.size)
+    if n != out.size:
+        _lib.check(int(n) if n < 0 else -1, f"stx_get_table({name})")
+    return out
+
+
+def peak_abs(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+    """max(1, max|x|) per clip as float32 [B] (the divisor of R/processor.py:91-92)."""
+    lib = _lib.load()
+    _require_cuda(pcm, "pcm", torch.float32)
+    _require_cuda(offsets, "offsets", torch.int64)
+    _require_cuda(lengths, "lengths", torch.int32)
+    B = lengths.numel()
+    peak = torch.empty(B, dtype=torch.float32, device=pcm.device)
+    with torch.cuda.device(pcm.device):
+        _lib.check(lib.stx_peak_abs(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, peak.data_ptr(),
+                                    _stream_ptr(pcm.device)), "stx_peak_abs")
+    return peak
+
+
+def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_length: int, T_pad: int,
+            padding_value: float = 0.0, normalize: bool = True, peak: torch.Tensor | None = None,
+            want_mask: bool = True, out: torch.Tensor | None = None, mask: torch.Tensor | None = None):
+    """Recipe K on device-resident packed PCM.
+
+    pcm float32 [total], offsets int64 [B], lengths int32 [B] (all CUDA); ``max_length`` is the host's
+    max over lengths.  Returns (input_features float32 [B, T_pad/2, 160], attention_mask int32
+    [B, T_pad/2] or None).
+    """
+    lib = _lib.load()
+    _require_cuda(pcm, "pcm", torch.float32)
+    _require_cuda(offsets, "offsets", torch.int64)
+    _require_cuda(lengths, "lengths", torch.int32)
+    if T_pad < 0 or T_pad % 2:
+        raise ValueError("T_pad must be even and >= 0")
+    B = lengths.numel()
+    dev = pcm.device
+    if out is None:
+        out = torch.empty((B, T_pad // 2, 2 * K_NMEL), dtype=torch.float32, device=dev)
+    else:
+        _require_cuda(out, "out", torch.float32)
+        if out.numel() != B * T_pad * K_NMEL:
+            raise ValueError("out has the wrong size")
+    if want_mask and mask is None:
+        mask = torch.empty((B, T_pad // 2), dtype=torch.int32, device=dev)
+    if mask is not None:
+        _require_cuda(mask, "mask", torch.int32)
+    if peak is not None:
+        _require_cuda(peak, "peak", torch.float32)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_fbank_k_workspace(B, int(max_length), C.byref(nbytes)), "stx_fbank_k_workspace")
+    ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_fbank_k(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, int(max_length),
+                                   peak.data_ptr() if peak is not None else None, int(T_pad),
+                                   float(padding_value), int(bool(normalize)), out.data_ptr(),
+                                   mask.data_ptr() if mask is not None else None, ws.data_ptr(), ws.numel(),
+                                   _stream_ptr(dev)), "stx_fbank_k")
+    return out, mask
+
+
+def logmel_w(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, n_samples: int = 480000,
+             want_mask: bool = False, peak: torch.Tensor | None = None, out: torch.Tensor | None = None):
+    """Recipe W on device-resident packed PCM -> (float32 [B, 80, n_samples/160], int32 mask or None)."""
+    lib = _lib.load()
+    _require_cuda(pcm, "pcm", torch.float32)
+    _require_cuda(offsets, "offsets", torch.int64)
+    _require_cuda(lengths, "lengths", torch.int32)
+    B = lengths.numel()
+    dev = pcm.device
+    T = n_samples // W_HOP
+    if out is None:
+        out = torch.empty((B, W_NMEL, T), dtype=torch.float32, device=dev)
+    else:
+        _require_cuda(out, "out", torch.float32)
+    mask = torch.empty((B, T), dtype=torch.int32, device=dev) if want_mask else None
+    if peak is not None:
+        _require_cuda(peak, "peak", torch.float32)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_logmel_w_workspace(B, int(n_samples), C.byref(nbytes)), "stx_logmel_w_workspace")
+    ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_logmel_w(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, int(n_samples),
+                                    peak.data_ptr() if peak is not None else None, out.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                    ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "stx_logmel_w")
+    return out, mask
+
+
+def _cosine_ws(N: int, M: int, D: int, dev) -> torch.Tensor:
+    lib = _lib.load()
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_cosine_workspace(N, M, D, C.byref(nbytes)), "stx_cosine_workspace")
+    return torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+
+
+def cosine_pairwise(a: torch.Tensor, b: torch.Tensor, always_normalize: bool = False) -> torch.Tensor:
+    """s[i] = <normalize(a_i), normalize(b_i)>, float32 [N] (R/processor.py:148-159)."""
+    lib = _lib.load()
+    _require_cuda(a, "a", torch.float32)
+    _require_cuda(b, "b", torch.float32)
+    if a.dim() != 2 or a.shape != b.shape:
+        raise ValueError(f"expected two [N, D] tensors of equal shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+    N, D = a.shape
+    s = torch.empty(N, dtype=torch.float32, device=a.device)
+    ws = _cosine_ws(N, N, D, a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.stx_cosine_pairwise(a.data_ptr(), b.data_ptr(), N, D, int(bool(always_normalize)),
+                                           s.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(a.device)),
+                   "stx_cosine_pairwise")
+    return s
+
+
+def cosine_nxm(a: torch.Tensor, b: torch.Tensor, always_normalize: bool = True,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """S[i, j] = <normalize(a_i), normalize(b_j)>, float32 [N, M]."""
+    lib = _lib.load()
+    _require_cuda(a, "a", torch.float32)
+    _require_cuda(b, "b", torch.float32)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError(f"expected [N, D] and [M, D], got {tuple(a.shape)} and {tuple(b.shape)}")
+    N, D = a.shape
+    M = b.shape[0]
+    if out is None:
+        out = torch.empty((N, M), dtype=torch.float32, device=a.device)
+    else:
+        _require_cuda(out, "out", torch.float32)
+        if out.shape != (N, M):
+            raise ValueError("out has the wrong shape")
+    ws = _cosine_ws(N, M, D, a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.stx_cosine_nxm(a.data_ptr(), b.data_ptr(), N, M, D, int(bool(always_normalize)),
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(a.device)),
+                   "stx_cosine_nxm")
+    return out

@@ -1,0 +1,137 @@
+"""Drop-in for the reference's ``AudioTextProcessor`` (R/processor.py:14-159), audio + scoring half.
+
+Same constructor arguments, same method names, same return dictionaries:
+
+  process_audio_array(audio_array, orig_sr) -> {"input_features": float32 [1, T', 160] on device,
+                                                "attention_mask_audio": int32 [1, T'] on device}
+  process_audio_file(path)                  -> same, after decoding the file
+  compute_similarity(e1, e2)                -> np.ndarray float32 [N]
+
+The float32 cast, the peak-normalise (R/processor.py:91-92) and the trim to ``max_audio_length``
+(:95-97) are kept; the feature extraction and the scoring run in libstx_b200.so.  Tokenisation, audio
+decoding and resampling are outside the hot path: they are delegated to the same third-party packages
+the reference uses and raise a clear error when those are not installed.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .feature_extraction import (B200SeamlessM4TFeatureExtractor, B200WhisperFeatureExtractor, PackedClips,
+                                 _layout)
+
+logger = logging.getLogger(__name__)
+
+
+def make_feature_extractor(audio_model_name: str, device=None, **kwargs):
+    """What ``AutoFeatureExtractor.from_pretrained(audio_model_name)`` resolves to for the two
+    front ends this repo implements (R/processor.py:36)."""
+    name = audio_model_name.lower()
+    if "whisper" in name:
+        return B200WhisperFeatureExtractor(device=device, **kwargs)
+    if "w2v-bert" in name or "seamless" in name or "wav2vec2-bert" in name:
+        return B200SeamlessM4TFeatureExtractor(device=device, **kwargs)
+    raise ValueError(f"no sm_100a front end for audio model {audio_model_name!r} "
+                     "(supported: facebook/w2v-bert-2.0 family, openai/whisper-*)")
+
+
+class AudioTextProcessor:
+    """Handles audio processing and scoring for the audio-text model on a B200."""
+
+    def __init__(self, text_model_name="sentence-transformers/all-roberta-large-v1",
+                 audio_model_name="facebook/w2v-bert-2.0", device=None, max_text_length=256,
+                 sampling_rate=16000, max_audio_length=480000, tokenizer=None, padding_value=0.0):
+        self.device = torch.device(device) if device is not None else torch.device(
+            "cuda" if torch.cuda.is_available() else "cpu")
+        self.max_text_length = max_text_length
+        self.sampling_rate = sampling_rate
+        self.max_audio_length = max_audio_length
+        self.text_model_name = text_model_name
+        self._tokenizer = tokenizer
+        fe_kwargs = {} if "whisper" in audio_model_name.lower() else {"padding_value": padding_value}
+        self.feature_extractor = make_feature_extractor(
+            audio_model_name, device=self.device if self.device.type == "cuda" else None, **fe_kwargs)
+        self._recipe_k = isinstance(self.feature_extractor, B200SeamlessM4TFeatureExtractor)
+        if self.device.type == "cuda":
+            # same start-up probe as the reference (R/processor.py:39-45)
+            dummy = self.feature_extractor(np.zeros(1000, dtype=np.float32), sampling_rate=self.sampling_rate,
+                                           return_tensors="pt")
+            logger.info(f"Feature extractor output keys: {list(dummy.keys())}")
+
+    # -- text (out of the hot path; same third-party tokenizer as the reference) ---------------
+    @property
+    def tokenizer(self):
+        if self._tokenizer is None:
+            from transformers import AutoTokenizer
+            self._tokenizer = AutoTokenizer.from_pretrained(self.text_model_name)
+        return self._tokenizer
+
+    def process_text(self, text):
+        enc = self.tokenizer(text, max_length=self.max_text_length, padding="max_length", truncation=True,
+                             return_tensors="pt")
+        return {"input_ids": enc["input_ids"].to(self.device), "attention_mask": enc["attention_mask"].to(self.device)}
+
+    # -- audio -----------------------------------------------------------------------------------
+    def process_audio_file(self, audio_path):
+        try:
+            import librosa
+        except ImportError as e:  # decoding is the step before the hot path
+            raise ImportError("process_audio_file needs librosa to decode audio files, as in the reference") from e
+        audio_array, orig_sr = librosa.load(audio_path, sr=None)
+        return self.process_audio_array(audio_array, orig_sr)
+
+    def _prepare(self, audio_array, orig_sr):
+        if orig_sr != self.sampling_rate:
+            try:
+                import librosa
+            except ImportError as e:
+                raise ImportError(f"resampling {orig_sr} Hz -> {self.sampling_rate} Hz needs librosa, as in the reference") from e
+            audio_array = librosa.resample(np.asarray(audio_array), orig_sr=orig_sr, target_sr=self.sampling_rate)
+        # NB the reference takes the peak over the untrimmed clip (R/processor.py:91-97); so do we:
+        # the trim happens on the device through the per-clip lengths
+        return np.ascontiguousarray(np.asarray(audio_array).astype(np.float32).reshape(-1))
+
+    def process_audio_array(self, audio_array, orig_sr):
+        return self.process_audio_batch([audio_array], orig_sr)
+
+    def process_audio_batch(self, audio_arrays, orig_sr):
+        """Batched form of process_audio_array (every clip gets its own peak-normalise and trim)."""
+        fe = self.feature_extractor
+        full = [self._prepare(a, orig_sr) for a in audio_arrays]
+        # peak over the whole clip (before the trim), division fused into the kernel's load
+        packed_full = fe.pack(full)
+        pcm_d, off_d, len_d = fe.to_device(packed_full)
+        peak = ops.peak_abs(pcm_d, off_d, len_d)
+        lengths = np.minimum(packed_full.lengths, self.max_audio_length).astype(np.int32)
+        len_trim = torch.from_numpy(lengths).to(pcm_d.device, non_blocking=True)
+        max_len = int(lengths.max()) if lengths.size else 0
+        if self._recipe_k:
+            frames = np.array([ops.k_num_frames(int(n)) for n in lengths], dtype=np.int64)
+            T_pad, _ = fe._padded_frames(frames, True, None, False, 2)
+            feats, mask = ops.fbank_k(pcm_d, off_d, len_trim, max_len, T_pad, fe.padding_value, True, peak=peak)
+        else:
+            feats, mask = ops.logmel_w(pcm_d, off_d, len_trim, fe.n_samples, want_mask=fe.return_attention_mask,
+                                       peak=peak)
+        return {"input_features": feats, "attention_mask_audio": mask}
+
+    # -- embeddings (consumer side; same as R/processor.py:128-146) ------------------------------
+    def get_text_embedding(self, model, text_input):
+        with torch.no_grad():
+            emb, _ = model.encode_text(text_input["input_ids"], text_input["attention_mask"])
+            return F.normalize(emb, p=2, dim=1)
+
+    def get_audio_embedding(self, model, audio_input):
+        with torch.no_grad():
+            emb, _ = model.encode_audio(audio_input["input_features"], audio_input["attention_mask_audio"])
+            return F.normalize(emb, p=2, dim=1)
+
+    # -- scoring ---------------------------------------------------------------------------------
+    def compute_similarity(self, embedding1, embedding2):
+        """Pairwise cosine similarity, np.float32 [N] (R/processor.py:148-159)."""
+        e1 = embedding1.to(self.device, torch.float32).contiguous()
+        e2 = embedding2.to(self.device, torch.float32).contiguous()
+        return ops.cosine_pairwise(e1, e2, always_normalize=False).cpu().numpy()

@@ -1,0 +1,138 @@
+"""GPU parity tests for recipe K (through the C ABI via the drop-in extractor).
+
+Bar (BASELINE.json north_star): max-abs error <= 1e-4 on input_features, attention masks bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import fbank_k as OK
+from speech_transcript_embeddings_b200 import ops, synth
+from speech_transcript_embeddings_b200.feature_extraction import B200SeamlessM4TFeatureExtractor
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def fe(cuda_device):
+    return B200SeamlessM4TFeatureExtractor(device=cuda_device)
+
+
+def _check(got, ref_x, ref_m, tol=TOL):
+    x, m = got["input_features"], got["attention_mask"]
+    assert x.shape == ref_x.shape and x.dtype == np.float32
+    assert m.shape == ref_m.shape and m.dtype == np.int32
+    assert np.array_equal(m, ref_m)
+    assert np.array_equal(np.isnan(x), np.isnan(ref_x))
+    err = np.nanmax(np.abs(x - ref_x)) if x.size else 0.0
+    assert err <= tol, f"max-abs error {err:.3e} > {tol}"
+    return err
+
+
+@pytest.mark.parametrize("kind", synth.GATED_CLASSES)
+def test_signal_classes_single_clip(fe, kind):
+    c = synth.clip(kind, 48000 + 37, seed=11)
+    ref = OK.extract([c])
+    err = _check(fe(c, sampling_rate=16000, return_tensors="np"), *ref)
+    print(f"K {kind}: max-abs {err:.2e}")
+
+
+def test_golden_fixtures(fe):
+    g = load_golden("fbank_k.npz")
+    n = int(g["n_clips"])
+    clips = [g[f"pcm_{i}"] for i in range(n)]
+    for i, c in enumerate(clips):
+        _check(fe(c, sampling_rate=16000, return_tensors="np"), g[f"feat_{i}"], g[f"mask_{i}"])
+    for pv in (0, 1):
+        fe_pv = B200SeamlessM4TFeatureExtractor(padding_value=float(pv), device=fe.device)
+        _check(fe_pv(clips[:6], sampling_rate=16000, return_tensors="np"), g[f"batch_feat_pv{pv}"], g[f"batch_mask_pv{pv}"])
+    got = fe(clips[0], sampling_rate=16000, return_tensors="np", do_normalize_per_mel_bins=False)
+    _check(got, g["raw_feat_0"], g["mask_0"], tol=4e-6)       # raw log-mel: within 2 float32 ulps at ~20
+    got = fe(np.zeros(1000, np.float32), sampling_rate=16000, return_tensors="np")
+    _check(got, g["probe_feat"], g["probe_mask"], tol=0.0)    # the reference's start-up probe: exact zeros
+
+
+def test_cfg1_one_30s_clip(fe):
+    c = synth.clip("G", 480000, 0)
+    ref = OK.extract([c])
+    got = fe(c, sampling_rate=16000, return_tensors="pt")
+    assert got["input_features"].is_cuda and tuple(got["input_features"].shape) == (1, 1499, 160)
+    assert got["attention_mask"].dtype == torch.int32
+    err = _check({k: v.cpu().numpy() for k, v in got.items()}, *ref)
+    print(f"K cfg1: max-abs {err:.2e}")
+
+
+def test_variable_length_batch_masks_exact(fe):
+    clips = synth.batch_variable(24, seed=77, whole_seconds=False, max_s=6)
+    clips += [synth.clip("G", n, 500 + n) for n in (400, 559, 560, 719, 720, 721, 879, 880)]   # T = 1..4, odd/even
+    with np.errstate(all="ignore"):
+        ref = OK.extract(clips)
+    _check(fe(clips, sampling_rate=16000, return_tensors="np"), *ref)
+
+
+def test_padding_options(fe):
+    clips = synth.batch_variable(5, seed=5, whole_seconds=False, max_s=3)
+    for kw in (dict(padding="max_length", max_length=400), dict(padding="longest", max_length=120, truncation=True),
+               dict(pad_to_multiple_of=None), dict(pad_to_multiple_of=8)):
+        ref = OK.extract(clips, pad_to_multiple_of=kw.get("pad_to_multiple_of", 2), max_length=kw.get("max_length"),
+                         truncation=kw.get("truncation", False), padding=kw.get("padding", "longest"))
+        _check(fe(clips, sampling_rate=16000, return_tensors="np", **kw), *ref)
+    got = fe(clips, sampling_rate=16000, return_tensors="np", return_attention_mask=False)
+    assert "attention_mask" not in got
+
+
+def test_too_short_clip_in_batch_is_all_padding(fe):
+    clips = [synth.clip("G", 16000, 1), np.zeros(399, np.float32) + 0.5]
+    got = fe(clips, sampling_rate=16000, return_tensors="np")
+    ref = OK.extract([clips[0]])
+    assert np.abs(got["input_features"][0] - ref[0][0]).max() <= TOL
+    assert not got["input_features"][1].any() and not got["attention_mask"][1].any()
+
+
+def test_input_types(fe):
+    c = synth.clip("G", 20000, 3)
+    ref = OK.extract([c])
+    stereo_batch = np.stack([c, np.zeros_like(c)])[None]               # [1, 2, n]: one stereo clip, channel 0 is used
+    for inp in (c.astype(np.float64), c.tolist(), torch.from_numpy(c), stereo_batch, [c]):
+        _check(fe(inp, sampling_rate=16000, return_tensors="np"), *ref)
+
+
+def test_cfg2_full_size_properties(fe):
+    """64 x 30 s: CMVN invariants over the whole batch, batch-invariance, oracle on a sample of clips."""
+    clips = synth.batch_fixed(64, 30.0, "G", 0)
+    got = fe(clips, sampling_rate=16000, return_tensors="pt")
+    x = got["input_features"]
+    assert tuple(x.shape) == (64, 1499, 160) and int(got["attention_mask"].sum()) == 64 * 1499
+    raw = x.reshape(64, 2998, 80).double()
+    assert raw.mean(dim=1).abs().max().item() < 1e-5                 # zero mean per clip and bin
+    assert (raw.var(dim=1, unbiased=True) - 1.0).abs().max().item() < 1e-4
+    for i in (0, 31, 63):
+        alone = fe(clips[i], sampling_rate=16000, return_tensors="pt")["input_features"]
+        assert torch.equal(alone[0], x[i])                            # a clip does not depend on its batch
+    worst = 0.0
+    for i in (0, 17, 42, 63):
+        ref = OK.extract([clips[i]])[0][0]
+        worst = max(worst, float(np.abs(x[i].cpu().numpy() - ref).max()))
+    print(f"K cfg2 sample of 4 clips: max-abs {worst:.2e}")
+    assert worst <= TOL
+
+
+def test_ill_conditioned_classes_are_reported_not_gated(fe):
+    for kind in synth.REPORTED_CLASSES:
+        c = synth.clip(kind, 48000, 0)
+        ref = OK.extract([c])
+        got = fe(c, sampling_rate=16000, return_tensors="np")
+        assert np.array_equal(got["attention_mask"], ref[1])
+        print(f"K {kind} (reported only): max-abs {np.abs(got['input_features'] - ref[0]).max():.2e}")
+
+
+def test_device_resident_entry_point(fe, cuda_device):
+    clips = synth.batch_variable(6, seed=9, whole_seconds=True, max_s=4)
+    packed = fe.pack(clips)
+    pcm, off, ln = fe.to_device(packed)
+    T_pad = 2 * ((max(ops.k_num_frames(c.size) for c in clips) + 1) // 2)
+    x, m = ops.fbank_k(pcm, off, ln, packed.max_length, T_pad)
+    ref = OK.extract(clips)
+    _check({"input_features": x.cpu().numpy(), "attention_mask": m.cpu().numpy()}, *ref)

@@ -1,0 +1,82 @@
+"""CPU: host-side logic of the drop-in (padding rules, packing, sharding, error behaviour)."""
+import numpy as np
+import pytest
+
+from oracle import fbank_k as OK
+from speech_transcript_embeddings_b200 import ops, sharding, synth
+from speech_transcript_embeddings_b200.feature_extraction import (B200SeamlessM4TFeatureExtractor,
+                                                                  B200WhisperFeatureExtractor, BatchFeature,
+                                                                  _as_clip_list, _layout)
+
+
+@pytest.mark.parametrize("lengths", [[16000], [16160, 400, 48000], [719, 720, 721], [399, 16000]])
+def test_padded_frames_match_oracle_shapes(lengths):
+    clips = [np.zeros(n, np.float32) + 0.01 * np.arange(n, dtype=np.float32) % 1 for n in lengths]
+    frames = np.array([ops.k_num_frames(n) for n in lengths])
+    assert [max(OK.num_frames(n), 0) for n in lengths] == list(frames)
+    T_pad, _ = B200SeamlessM4TFeatureExtractor._padded_frames(frames, True, None, False, 2)
+    if min(lengths) >= 400:
+        with np.errstate(all="ignore"):
+            x, m = OK.extract(clips)
+        assert x.shape[1] * 2 == T_pad and m.shape[1] * 2 == T_pad
+
+
+def test_padding_strategies():
+    f = np.array([99, 10, 300])
+    pf = B200SeamlessM4TFeatureExtractor._padded_frames
+    assert pf(f, True, None, False, 2)[0] == 300
+    assert pf(np.array([99]), True, None, False, 2)[0] == 100
+    assert pf(np.array([99]), True, None, False, None)[0] == 98       # remainder frame dropped (…seamless_m4t.py:281-285)
+    assert pf(f, "max_length", 401, False, 2)[0] == 402
+    T_pad, kept = pf(f, "longest", 100, True, 2)
+    assert T_pad == 100 and list(kept) == [99, 10, 100]
+    with pytest.raises(ValueError):
+        pf(f, False, None, False, 2)
+    with pytest.raises(ValueError):
+        pf(f, "max_length", 100, False, 2)
+
+
+def test_layout_is_128_byte_aligned_and_disjoint():
+    lengths = np.array([1, 31, 32, 33, 480000, 5], np.int32)
+    off, total = _layout(lengths)
+    assert (off % 32 == 0).all() and off[0] == 0
+    assert (off[1:] >= off[:-1] + lengths[:-1]).all() and total >= off[-1] + lengths[-1]
+
+
+def test_batching_rules():
+    one = _as_clip_list(np.zeros(1000, np.float64), 3, "X")
+    assert len(one) == 1 and one[0].dtype == np.float32
+    assert len(_as_clip_list([0.0] * 500, 3, "X")) == 1
+    assert len(_as_clip_list([np.zeros(500), np.zeros(700)], 3, "X")) == 2
+    assert len(_as_clip_list(np.zeros((3, 500)), 3, "X")) == 3
+    stereo = _as_clip_list([np.stack([np.ones(500), np.zeros(500)])], 3, "X")
+    assert stereo[0].shape == (500,) and stereo[0].all()
+    with pytest.raises(ValueError):
+        _as_clip_list(np.zeros((2, 2, 2, 2)), 3, "X")
+
+
+def test_sampling_rate_errors_and_ctor_guards():
+    fe = B200SeamlessM4TFeatureExtractor(device=None)
+    with pytest.raises(ValueError, match="16000"):
+        fe(np.zeros(1000, np.float32), sampling_rate=8000)
+    with pytest.raises(ValueError):
+        B200SeamlessM4TFeatureExtractor(num_mel_bins=40)
+    with pytest.raises(ValueError):
+        B200WhisperFeatureExtractor(n_fft=512)
+
+
+def test_batch_feature_protocol():
+    bf = BatchFeature({"input_features": 1, "attention_mask": 2})
+    assert "input_features" in bf and bf["attention_mask"] == 2 and bf.get("nope") is None
+    assert list(bf.keys()) == ["input_features", "attention_mask"] and bf.input_features == 1
+
+
+def test_shard_clips_partitions_and_balances():
+    lens = synth.variable_lengths(512, seed=1234)
+    shards = sharding.shard_clips(lens, 8)
+    allidx = np.sort(np.concatenate(shards))
+    assert np.array_equal(allidx, np.arange(512))
+    load = np.array([lens[s].sum() for s in shards])
+    assert load.max() / load.mean() < 1.01
+    parts = [lens[s][:, None] for s in shards]
+    assert np.array_equal(sharding.unshard(parts, shards)[:, 0], lens)

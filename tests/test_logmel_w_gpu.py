@@ -1,0 +1,61 @@
+"""GPU parity tests for recipe W (Whisper log-mel) through the C ABI.  Bar: max-abs <= 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import logmel_w as OW
+from speech_transcript_embeddings_b200 import synth
+from speech_transcript_embeddings_b200.feature_extraction import B200WhisperFeatureExtractor
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def fe(cuda_device):
+    return B200WhisperFeatureExtractor(device=cuda_device)
+
+
+def test_golden_fixtures(fe):
+    g = load_golden("logmel_w.npz")
+    clips = [g[f"pcm_{i}"] for i in range(int(g["n_clips"]))]
+    got = fe(clips, sampling_rate=16000, return_tensors="np", max_length=16000, return_attention_mask=True)
+    assert got["input_features"].shape == (3, 80, 100) and got["input_features"].dtype == np.float32
+    assert np.abs(got["input_features"] - g["feat_ml16000"]).max() <= TOL
+    assert np.array_equal(got["attention_mask"], g["mask_ml16000"]) and got["attention_mask"].dtype == np.int32
+    got = fe(clips[1], sampling_rate=16000, return_tensors="np")
+    assert got["input_features"].shape == (1, 80, 3000) and "attention_mask" not in got
+    assert np.abs(got["input_features"][:, :, ::25] - g["feat_stock_1"]).max() <= TOL
+    assert np.abs(got["input_features"][:, :, -4:] - g["feat_stock_1_tail"]).max() <= TOL
+
+
+@pytest.mark.parametrize("kind", synth.GATED_CLASSES + synth.REPORTED_CLASSES)
+def test_signal_classes(fe, kind):
+    c = synth.clip(kind, 100000 + 13, seed=21)
+    ref, _ = OW.extract([c])
+    got = fe(c, sampling_rate=16000, return_tensors="np")["input_features"]
+    err = np.abs(got - ref).max()
+    print(f"W {kind}: max-abs {err:.2e}")
+    assert err <= TOL
+
+
+def test_truncation_and_batch(fe):
+    clips = [synth.clip("G", 500000, 1), synth.clip("U", 480000, 2), synth.clip("AM", 7, 3), synth.clip("G", 479999, 4)]
+    ref, rm = OW.extract(clips, return_attention_mask=True)
+    got = fe(clips, sampling_rate=16000, return_tensors="np", return_attention_mask=True)
+    assert np.abs(got["input_features"] - ref).max() <= TOL
+    assert np.array_equal(got["attention_mask"], rm)
+
+
+def test_full_size_properties(fe):
+    clips = synth.batch_fixed(64, 30.0, "G", 100)
+    x = fe(clips, sampling_rate=16000, return_tensors="pt")["input_features"]
+    assert tuple(x.shape) == (64, 80, 3000) and x.is_cuda
+    mx = x.amax(dim=(1, 2))
+    mn = x.amin(dim=(1, 2))
+    assert bool((mn >= mx - 2.0 - 1e-6).all())                       # max(x, max - 8) then /4
+    alone = fe(clips[5], sampling_rate=16000, return_tensors="pt")["input_features"]
+    assert torch.equal(alone[0], x[5])
+    ref, _ = OW.extract([clips[5]])
+    assert np.abs(x[5].cpu().numpy() - ref[0]).max() <= TOL

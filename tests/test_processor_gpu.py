@@ -1,0 +1,56 @@
+"""GPU: the AudioTextProcessor drop-in (R/processor.py:79-159) against the reference's own steps
+restated with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cosine as OC
+from oracle import fbank_k as OK
+from oracle import logmel_w as OW
+from speech_transcript_embeddings_b200 import synth
+from speech_transcript_embeddings_b200.processor import AudioTextProcessor
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference_prepare(audio, max_audio_length):
+    """R/processor.py:88-97."""
+    a = audio.astype(np.float32)
+    if np.abs(a).max() > 1.0:
+        a = a / np.abs(a).max()
+    return a[:max_audio_length]
+
+
+@pytest.mark.parametrize("kind", ["loud", "G", "AM"])
+def test_process_audio_array_recipe_k(cuda_device, kind):
+    proc = AudioTextProcessor(device=cuda_device, max_audio_length=40000)
+    audio = synth.clip(kind, 52345, seed=8)
+    out = proc.process_audio_array(audio, 16000)
+    assert set(out) == {"input_features", "attention_mask_audio"}
+    ref_x, ref_m = OK.extract([_reference_prepare(audio, 40000)])
+    x, m = out["input_features"], out["attention_mask_audio"]
+    assert x.device == cuda_device and x.dtype == torch.float32 and m.dtype == torch.int32
+    assert tuple(x.shape) == ref_x.shape and np.array_equal(m.cpu().numpy(), ref_m)
+    assert np.abs(x.cpu().numpy() - ref_x).max() <= 1e-4
+
+
+def test_process_audio_array_recipe_w(cuda_device):
+    proc = AudioTextProcessor(audio_model_name="openai/whisper-small", device=cuda_device)
+    audio = synth.clip("loud", 30000, seed=9)
+    out = proc.process_audio_array(audio, 16000)
+    ref, _ = OW.extract([_reference_prepare(audio, 480000)])
+    assert out["attention_mask_audio"] is None
+    assert np.abs(out["input_features"].cpu().numpy() - ref).max() <= 1e-4
+
+
+def test_compute_similarity(cuda_device):
+    proc = AudioTextProcessor(device=cuda_device)
+    a, b = synth.embedding_pairs(8, 1024, seed=5)
+    s = proc.compute_similarity(torch.from_numpy(a * 2).to(cuda_device), torch.from_numpy(b).to(cuda_device))
+    assert isinstance(s, np.ndarray) and s.dtype == np.float32 and s.shape == (8,)
+    assert np.abs(s - OC.pairwise_reference(a * 2, b)).max() <= 1e-5
+
+
+def test_unsupported_audio_model_is_an_error(cuda_device):
+    with pytest.raises(ValueError):
+        AudioTextProcessor(audio_model_name="facebook/wav2vec2-base", device=cuda_device)
