@@ -56,6 +56,13 @@ const char* stx_last_error(void);
  * `gpu_launches` is the difference of this counter across the timed region. */
 uint64_t    stx_kernel_launch_count(void);
 
+/* Per-launch timing for bench.py's roofline leg.  While enabled, every kernel launch of the library
+ * is bracketed by CUDA events on its own stream.  stx_profile_collect synchronises on those events,
+ * writes up to `cap` records (kernel name, 32 bytes each, NUL-terminated; elapsed milliseconds), clears
+ * the log and returns the number of records written. */
+int         stx_profile_enable(int on);
+int         stx_profile_collect(char* h_names, float* h_ms, int cap);
+
 /* Copies a host-side float64 table used by the kernels, for inspection by tests.
  *   "k_window"  [400]      Povey window                      (TF/audio_utils.py:593, 601-602)
  *   "k_mel"     [257*80]   Kaldi mel filters, row-major      (TF/audio_utils.py:516-530)

@@ -15,6 +15,8 @@ _SIGNATURES = {
     "stx_abi_version": (C.c_int, []),
     "stx_last_error": (C.c_char_p, []),
     "stx_kernel_launch_count": (C.c_uint64, []),
+    "stx_profile_enable": (C.c_int, [C.c_int]),
+    "stx_profile_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "stx_get_table": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64]),
     "stx_fbank_k_workspace": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "stx_fbank_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
@@ -65,6 +67,19 @@ def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().stx_last_error().decode(errors="replace")
         raise StxError(f"{what} failed (rc={rc}): {msg}")
+
+
+def profile(on: bool) -> None:
+    load().stx_profile_enable(int(bool(on)))
+
+
+def profile_collect(cap: int = 65536):
+    """[(kernel name, milliseconds), ...] of the launches since profiling was enabled (synchronises)."""
+    lib = load()
+    names = C.create_string_buffer(32 * cap)
+    ms = (C.c_float * cap)()
+    n = lib.stx_profile_collect(names, ms, cap)
+    return [(names.raw[32 * i:32 * (i + 1)].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n)]
 
 
 def launch_count() -> int:

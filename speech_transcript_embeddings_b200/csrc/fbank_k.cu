@@ -299,9 +299,11 @@ __global__ void k_finalize(const int* __restrict__ lengths, const double* __rest
         a2 += p[kMel + m];
     }
     const double mean = a1 / (double)T;
-    const double var = (a2 - a1 * mean) / (double)(T - 1);        // T == 1 -> 0/0 = NaN, like numpy's ddof=1
+    // a single frame has no ddof=1 variance: numpy returns NaN there and so do we
+    double var = T > 1 ? (a2 - a1 * mean) / (double)(T - 1) : __longlong_as_double(0x7ff8000000000000LL);
+    if (var < 0.0) var = 0.0;                                      // rounding of a constant column; keeps NaN
     stats[((size_t)b * kMel + m) * 2 + 0] = mean;
-    stats[((size_t)b * kMel + m) * 2 + 1] = 1.0 / sqrt(fmax(var, 0.0) + 1e-7);
+    stats[((size_t)b * kMel + m) * 2 + 1] = 1.0 / sqrt(var + 1e-7);
 }
 
 // in-place CMVN + padding rows + mask.  One thread per float4 of a clip's [T_pad, 80] block.

@@ -24,6 +24,27 @@ int cuda_fail(cudaError_t e, const char* what) {
     return static_cast<int>(e);
 }
 
+// ---- per-launch timing -----------------------------------------------------------------
+std::atomic<int> g_profile{0};
+namespace {
+struct ProfRec { const char* name; cudaEvent_t start, stop; };
+std::mutex g_prof_mutex;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+void profile_before(const char* name, cudaStream_t st) {
+    ProfRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+    cudaEventRecord(r.start, st);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof.push_back(r);
+}
+
+void profile_after(cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (!g_prof.empty()) cudaEventRecord(g_prof.back().stop, st);
+}
+
 int check_device() {
     static std::atomic<int> cached{1};   // 1 = unknown
     int c = cached.load();
@@ -151,6 +172,29 @@ extern "C" {
 int stx_abi_version(void) { return STX_ABI_VERSION; }
 const char* stx_last_error(void) { return stx::t_error.c_str(); }
 uint64_t stx_kernel_launch_count(void) { return stx::g_launches.load(); }
+
+int stx_profile_enable(int on) {
+    stx::g_profile.store(on ? 1 : 0);
+    return 0;
+}
+
+int stx_profile_collect(char* h_names, float* h_ms, int cap) {
+    std::lock_guard<std::mutex> lock(stx::g_prof_mutex);
+    int n = 0;
+    for (auto& r : stx::g_prof) {
+        float ms = 0.0f;
+        if (r.stop && cudaEventSynchronize(r.stop) == cudaSuccess) cudaEventElapsedTime(&ms, r.start, r.stop);
+        if (n < cap && h_names && h_ms) {
+            snprintf(h_names + size_t(n) * 32, 32, "%s", r.name);
+            h_ms[n] = ms;
+            ++n;
+        }
+        if (r.start) cudaEventDestroy(r.start);
+        if (r.stop) cudaEventDestroy(r.stop);
+    }
+    stx::g_prof.clear();
+    return n;
+}
 
 int64_t stx_get_table(const char* name, double* h_out, int64_t cap) {
     if (!name || !h_out) { stx::set_error("stx_get_table: null argument"); return STX_EINVAL; }

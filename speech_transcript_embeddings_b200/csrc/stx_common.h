@@ -20,10 +20,19 @@ extern std::atomic<uint64_t> g_launches;
         if (e__ != cudaSuccess) return stx::cuda_fail(e__, #call); \
     } while (0)
 
+// Optional per-launch timing (stx_profile_enable): CUDA events recorded on the launching stream
+// immediately before and after each kernel; collected by stx_profile_collect.
+extern std::atomic<int> g_profile;
+void profile_before(const char* name, cudaStream_t st);
+void profile_after(cudaStream_t st);
+
 // every kernel launch of the library goes through this macro so that the launch counter is exact
 #define STX_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
     do {                                                                         \
+        const bool prof__ = stx::g_profile.load(std::memory_order_relaxed) != 0; \
+        if (prof__) stx::profile_before(#kernel, (stream));                      \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);              \
+        if (prof__) stx::profile_after((stream));                                \
         stx::g_launches.fetch_add(1, std::memory_order_relaxed);                 \
         cudaError_t e__ = cudaGetLastError();                                    \
         if (e__ != cudaSuccess) return stx::cuda_fail(e__, "launch " #kernel);   \
