@@ -274,7 +274,7 @@ def run_b200(args):
             pcm_d, off_d, len_d = dev_batches[i % POOL_BATCHES]
             ops.fbank_k(pcm_d, off_d, len_d, n, T_pad, out=outs[i % POOL_BATCHES], mask=masks[i % POOL_BATCHES])
         bytes_per_clip = K_BYTES_PER_CLIP
-        dominant = "k_frames"
+        dominant = "k_frames<false>"
     else:
         outs = [torch.empty((B, 80, n // 160), dtype=torch.float32, device=dev) for _ in range(POOL_BATCHES)]
 

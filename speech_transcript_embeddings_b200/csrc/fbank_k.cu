@@ -27,6 +27,7 @@
 //   power (after rounding X to float32, like the reference's complex64) -> sparse mel -> ln
 #include "stx_common.h"
 #include <cmath>
+#include <cstddef>
 #include <mutex>
 
 namespace stx {
@@ -40,9 +41,13 @@ constexpr int kThreads = kSlots * 16;            // 256
 constexpr int kChunk = 128;                      // frames per CTA
 constexpr int kWinPad = 416;                     // window zero-padded so that r + 16 j <= 207 stays in range
 constexpr int kSubSamples = (kSlots - 1) * kHop + kWinPad;   // 2816 = 11 * 256
-constexpr int kExRow = 17;                       // padded row of the 16 x 16 exchange (complex doubles)
 constexpr int kMelWeights = 512;                 // >= 501 non-zeros
 constexpr float kMelFloor = 1.192092955078125e-07f;
+constexpr int kStageLead = 4;                    // staging keeps 4 samples before the sub-tile (x[-1] and 16-byte alignment)
+constexpr int kStage = kSubSamples + kStageLead; // 2820 floats
+constexpr int kSlotFloats = 1024;                // one slot's exchange area (16 x 16 complex doubles) in floats
+constexpr int kPRowSkew = 1;                     // power spectrum of frame f starts f floats into its slot: banks (f + k) % 32
+constexpr int kOutRow = kSlotFloats + 17;        // staged log-mel row of frame f at 512 + 1041 f: banks (17 f + m) % 32
 
 struct KTables {
     double  win[kWinPad];        // 2^15 * Povey, zero beyond 400
@@ -53,17 +58,21 @@ struct KTables {
 };
 
 struct Smem {
-    double  dtile[kSubSamples];
+    double  dtile[kSubSamples];  // d[i] = x[i] - 0.97 x[i-1] of the current sub-tile (float64)
     double  win[kWinPad];
     double2 tw[256];
     double2 post[256];
+    double2 ex[kSlots * 256];    // 16 x 16 exchange per slot (XOR-swizzled); later aliased by the power
+                                 // spectra, the staged log-mel rows and the statistics reduction
+    float   stage[kStage + 12];  // raw PCM of the NEXT sub-tile, landed by cp.async.bulk (TMA) while this one computes
     float   melw[kMelWeights];
     int     melmeta[kMel];
     double  xb0[kSlots];         // x[160 f]       of each frame of the sub-tile
     double  xb1[kSlots];         // x[160 f + 399]
-    double2 ex[kSlots * 16 * kExRow];   // exchange; aliased by the power spectrum and the stats reduction
+    unsigned long long mbar;     // completion barrier of the bulk copy
 };
-static_assert(sizeof(Smem) <= 110 * 1024, "two CTAs per SM must fit");
+static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs per SM must fit in 228 KB");
+static_assert(offsetof(Smem, stage) % 16 == 0 && offsetof(Smem, ex) % 16 == 0, "bulk-copy / vector alignment");
 
 struct cd { double re, im; };
 __device__ __forceinline__ cd operator+(cd a, cd b) { return {a.re + b.re, a.im + b.im}; }
@@ -122,12 +131,43 @@ __device__ __forceinline__ void dft16(const cd (&v)[16], cd (&o)[16]) {
         dft4(b[0][k1], b[1][k1], b[2][k1], b[3][k1], o[k1], o[k1 + 4], o[k1 + 8], o[k1 + 12]);
 }
 
-__device__ __forceinline__ float load_sample(const float* __restrict__ pcm, long long g, int n, float peak) {
-    if (g < 0 || g >= n) return 0.0f;
-    float v = __ldg(pcm + g);
-    return peak != 1.0f ? v / peak : v;   // float32 division, like numpy's (R/processor.py:92)
+// ---- mbarrier + 1-D bulk copy (TMA) ---------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// Samples [lo, hi) of the clip that the bulk copy stages for the sub-tile starting at sample s0
+// (stage[kStageLead + i] = x[s0 + i]).  Both ends are multiples of 4 samples so that the copy is
+// 16-byte aligned and sized; everything else (the <= 3 tail samples of a clip, or the whole range when
+// the clip is not 16-byte aligned in memory) is read with plain loads in the pre-pass.
+struct StageRange { int lo, hi; };
+__device__ __forceinline__ StageRange stage_range(int s0, int n, bool aligned) {
+    StageRange r;
+    r.lo = max(s0 - kStageLead, 0);
+    r.hi = aligned ? min(s0 + kSubSamples, n & ~3) : r.lo;
+    if (r.hi < r.lo) r.hi = r.lo;
+    return r;
+}
+
+template <bool kPeak>
 __global__ void __launch_bounds__(kThreads, 2)
 k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
          const float* __restrict__ peaks, const KTables* __restrict__ tab, int T_pad, int chunks_per_clip,
@@ -143,7 +183,8 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     if (t_begin >= T) return;                       // uniform per CTA
     const int t_end = min(T, t_begin + kChunk);
     const float* clip = pcm + offsets[b];
-    const float peak = peaks ? peaks[b] : 1.0f;
+    const bool aligned = (reinterpret_cast<unsigned long long>(clip) & 15ull) == 0;
+    const float peak = kPeak ? peaks[b] : 1.0f;
     float* out_b = out + (size_t)b * T_pad * kMel;
 
     const int tid = threadIdx.x;
@@ -151,36 +192,64 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     const int r = tid & 15;
     const int lane = tid & 31;
 
+    // first sub-tile's PCM: issue the bulk copy before anything else
+    if (tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        const StageRange sr = stage_range(t_begin * kHop, n, aligned);
+        if (sr.hi > sr.lo) {
+            mbar_expect_tx(&sm.mbar, (unsigned)(sr.hi - sr.lo) * 4u);
+            bulk_g2s(sm.stage + (sr.lo - (t_begin * kHop - kStageLead)), clip + sr.lo, (unsigned)(sr.hi - sr.lo) * 4u, &sm.mbar);
+        }
+    }
     // tables -> shared
     for (int i = tid; i < kWinPad; i += kThreads) sm.win[i] = tab->win[i];
     sm.tw[tid] = tab->tw[tid];
     sm.post[tid] = tab->post[tid];
     for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
     if (tid < kMel) sm.melmeta[tid] = tab->melmeta[tid];
+    __syncthreads();                                // mbarrier init + tables visible
 
+    // mel stage mapping: lane <-> frame, 16 groups of 5 mel bins (g, g + 16, ..., g + 64)
+    const int mf = tid & 15, mg = tid >> 4;
     double s1[5], s2[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) s1[i] = s2[i] = 0.0;
+    float* exf = reinterpret_cast<float*>(sm.ex);
+    unsigned parity = 0;
 
     for (int t0 = t_begin; t0 < t_end; t0 += kSlots) {
-        __syncthreads();                            // previous sub-tile fully consumed (and tables visible)
-        // ---- pre-pass: d[i] = x[i] - 0.97 x[i-1] in float64 for the 2816 samples of 16 frames ----
-        const long long s0 = (long long)t0 * kHop;
+        // ---- pre-pass: staged PCM -> d[i] = x[i] - 0.97 x[i-1] (float64) ----
+        const int s0 = t0 * kHop;
+        const StageRange sr = stage_range(s0, n, aligned);
+        if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
+        auto sample = [&](int g) -> float {          // x[g] of this clip, 0 outside
+            float v = 0.0f;
+            if (g >= sr.lo && g < sr.hi) v = sm.stage[g - s0 + kStageLead];
+            else if (g >= 0 && g < n) v = __ldg(clip + g);
+            if (kPeak) v = v / peak;                  // float32 division, like numpy's (R/processor.py:92)
+            return v;
+        };
 #pragma unroll
         for (int u = 0; u < kSubSamples / kThreads; ++u) {
             const int i = tid + u * kThreads;
-            const long long g = s0 + i;
-            const double x = (double)load_sample(clip, g, n, peak);
-            const double xm = (double)load_sample(clip, g - 1, n, peak);
+            const double x = (double)sample(s0 + i);
+            const double xm = (double)sample(s0 + i - 1);
             sm.dtile[i] = fma(-0.97, xm, x);
             const int f = i / kHop, rem = i - f * kHop;
             if (rem == 0 && f < kSlots) sm.xb0[f] = x;
             if (rem == 79 && f >= 2) sm.xb1[f - 2] = x;          // 399 = 2 * 160 + 79
         }
-        __syncthreads();
+        __syncthreads();                            // dtile ready; staging and the exchange area are free again
 
-        const int t = t0 + slot;
-        const bool active = t < t_end;
+        // next sub-tile's PCM lands while this one is transformed
+        if (tid == 0 && t0 + kSlots < t_end) {
+            const StageRange nx = stage_range(s0 + kSlots * kHop, n, aligned);
+            if (nx.hi > nx.lo) {
+                mbar_expect_tx(&sm.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
+                bulk_g2s(sm.stage + (nx.lo - (s0 + kSlots * kHop - kStageLead)), clip + nx.lo,
+                         (unsigned)(nx.hi - nx.lo) * 4u, &sm.mbar);
+            }
+        }
 
         // ---- frame -> y (float64) ----
         const double2* dfr = reinterpret_cast<const double2*>(sm.dtile + slot * kHop);
@@ -209,30 +278,30 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             v[j].im = w.y * (v[j].im - c);
         }
 
-        // ---- pass 1 ----
+        // ---- pass 1 ----  exchange element (row k1, column n2) lives at k1 * 16 + (n2 ^ (k1 & 7))
         cd a[16];
         dft16<true>(v, a);
-        double2* ex = sm.ex + slot * 16 * kExRow;
+        double2* ex = sm.ex + slot * 256;
         ex[r] = make_double2(a[0].re, a[0].im);
 #pragma unroll
         for (int k1 = 1; k1 < 16; ++k1) {
             double2 w = sm.tw[k1 * 16 + r];
             cd m = cmul(a[k1], w.x, w.y);
-            ex[k1 * kExRow + r] = make_double2(m.re, m.im);
+            ex[k1 * 16 + (r ^ (k1 & 7))] = make_double2(m.re, m.im);
         }
         __syncwarp();
 
         // ---- pass 2 (thread r now owns row k1 = r) ----
 #pragma unroll
         for (int n2 = 0; n2 < 16; ++n2) {
-            double2 p = ex[r * kExRow + n2];
+            double2 p = ex[r * 16 + (n2 ^ (r & 7))];
             v[n2] = {p.x, p.y};
         }
         dft16<false>(v, a);                          // a[k2] = Z[r + 16 k2]
-        __syncwarp();                                // all reads of ex done before it is reused for the power spectrum
+        __syncwarp();                                // the slot's exchange area is now free for its power spectrum
 
         // ---- real split + power ----
-        float* P = reinterpret_cast<float*>(ex);     // 256 floats per slot
+        float* P = exf + slot * (kSlotFloats + kPRowSkew);       // 256 floats, skewed by one float per slot
         const int partner = (lane & 16) | ((16 - r) & 15);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
@@ -241,38 +310,57 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             if (r == 0) { pr = a[(16 - k2) & 15].re; pi = a[(16 - k2) & 15].im; }
             const double2 w = sm.post[k2 * 16 + r];
             const double ar = a[k2].re, ai = a[k2].im;
-            const double sr = ar + pr, dr = ar - pr, si = ai + pi, di = ai - pi;
-            const double xr = fma(w.y, dr, fma(w.x, si, sr));       // 2 Re X[k]
+            const double sr_ = ar + pr, dr = ar - pr, si = ai + pi, di = ai - pi;
+            const double xr = fma(w.y, dr, fma(w.x, si, sr_));      // 2 Re X[k]
             const double xi = fma(w.y, si, fma(-w.x, dr, di));      // 2 Im X[k]
             const float fr = (float)xr, fi = (float)xi;             // the reference rounds X to complex64
             P[r + 16 * k2] = fmaf(fr, fr, fi * fi);                 // 4 |X|^2 (the 1/4 is in the mel weights)
         }
-        __syncwarp();
+        __syncthreads();                            // all 16 power spectra visible
 
-        // ---- sparse mel, ln, store, statistics ----
+        // ---- sparse mel + ln: lane <-> frame (weights broadcast, power spectra conflict-free) ----
+        {
+            const float* Pf = exf + mf * (kSlotFloats + kPRowSkew);
+            float* orow = exf + 512 + mf * kOutRow;
+            const bool active = t0 + mf < t_end;
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int m = r + 16 * i;
-            const int meta = sm.melmeta[m];
-            const int first = meta & 511, count = (meta >> 9) & 511, off = meta >> 18;
-            float acc = 0.0f;
-            for (int q = 0; q < count; ++q) acc = fmaf(sm.melw[off + q], P[first + q], acc);
-            const float lg = logf(fmaxf(acc, kMelFloor));
-            if (active) {
-                if (t < T_pad) out_b[(size_t)t * kMel + m] = lg;
-                s1[i] += (double)lg;
-                s2[i] = fma((double)lg, (double)lg, s2[i]);
+            for (int i = 0; i < 5; ++i) {
+                const int m = mg + 16 * i;
+                const int meta = sm.melmeta[m];
+                const int first = meta & 511, count = (meta >> 9) & 511, off = meta >> 18;
+                float acc = 0.0f;
+                for (int q = 0; q < count; ++q) acc = fmaf(sm.melw[off + q], Pf[first + q], acc);
+                const float lg = logf(fmaxf(acc, kMelFloor));
+                orow[m] = lg;
+                if (active) {
+                    s1[i] += (double)lg;
+                    s2[i] = fma((double)lg, (double)lg, s2[i]);
+                }
             }
         }
+        __syncthreads();                            // staged rows complete
+
+        // ---- coalesced store of the sub-tile's rows: frames t0 .. are one contiguous block of out ----
+        {
+            const int rows = min(min(t_end, T_pad) - t0, kSlots);
+            float* dst = out_b + (size_t)t0 * kMel;
+            for (int e = tid; e < rows * (kMel / 4); e += kThreads) {
+                const int f = e / (kMel / 4), m4 = (e - f * (kMel / 4)) * 4;
+                const float* src = exf + 512 + f * kOutRow + m4;
+                reinterpret_cast<float4*>(dst)[e] = make_float4(src[0], src[1], src[2], src[3]);
+            }
+        }
+        // the next iteration's pre-pass only touches dtile / xb / stage; its __syncthreads orders these
+        // reads of the exchange area before the next pass 1 overwrites it
     }
 
-    // ---- per-chunk statistics: ordered reduction over the 16 slots ----
+    // ---- per-chunk statistics: ordered reduction over the 16 frame lanes ----
     __syncthreads();
     double* red = reinterpret_cast<double*>(sm.ex);   // [2][16][80]
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        red[slot * kMel + r + 16 * i] = s1[i];
-        red[kSlots * kMel + slot * kMel + r + 16 * i] = s2[i];
+        red[mf * kMel + mg + 16 * i] = s1[i];
+        red[kSlots * kMel + mf * kMel + mg + 16 * i] = s2[i];
     }
     __syncthreads();
     if (tid < 2 * kMel) {
@@ -396,7 +484,8 @@ int get_tables(const KTables** out) {
         KTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(KTables)));
         STX_CUDA(cudaMemcpy(d, &h, sizeof(KTables), cudaMemcpyHostToDevice));
-        STX_CUDA(cudaFuncSetAttribute(k_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        STX_CUDA(cudaFuncSetAttribute(k_frames<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        STX_CUDA(cudaFuncSetAttribute(k_frames<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         g_tab[dev] = d;
     }
     *out = g_tab[dev];
@@ -441,9 +530,15 @@ int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_l
     double* stats = reinterpret_cast<double*>(static_cast<char*>(d_ws) +
                                               align256(size_t(B) * chunks * 2 * kMel * sizeof(double)));
     if (frames_of(max_length) > 0) {
-        STX_LAUNCH(k_frames, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
-                   d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad, chunks,
-                   d_out, partials);
+        if (d_peak) {
+            STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad, chunks,
+                       d_out, partials);
+        } else {
+            STX_LAUNCH(k_frames<false>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad, chunks,
+                       d_out, partials);
+        }
     }
     STX_LAUNCH(k_finalize, dim3(B), dim3(96), 0, st, d_lengths, partials, chunks, stats);
     const int quads = T_pad * (kMel / 4);

@@ -136,3 +136,19 @@ def test_device_resident_entry_point(fe, cuda_device):
     x, m = ops.fbank_k(pcm, off, ln, packed.max_length, T_pad)
     ref = OK.extract(clips)
     _check({"input_features": x.cpu().numpy(), "attention_mask": m.cpu().numpy()}, *ref)
+
+
+def test_unaligned_clip_offsets_take_the_plain_load_path(fe, cuda_device):
+    """Offsets that are not multiples of 4 samples cannot use the 16-byte bulk copy; results must not change."""
+    clips = [synth.clip("G", 16000 + 3 * i, 40 + i) for i in range(4)]
+    lengths = np.array([c.size for c in clips], np.int32)
+    offsets = np.array([1, 16000 + 6, 32000 + 3 + 13, 48010 + 40], np.int64)     # 1, 2, 3, 2 mod 4
+    buf = np.zeros(int(offsets[-1] + lengths[-1] + 8), np.float32)
+    for c, o in zip(clips, offsets):
+        buf[o:o + c.size] = c
+    pcm = torch.from_numpy(buf).to(cuda_device)
+    T_pad = 2 * ((max(ops.k_num_frames(int(n)) for n in lengths) + 1) // 2)
+    x, m = ops.fbank_k(pcm, torch.from_numpy(offsets).to(cuda_device), torch.from_numpy(lengths).to(cuda_device),
+                       int(lengths.max()), T_pad)
+    ref = OK.extract(clips)
+    _check({"input_features": x.cpu().numpy(), "attention_mask": m.cpu().numpy()}, *ref)
