@@ -41,12 +41,14 @@ constexpr int kThreads = kSlots * 16;            // 256
 constexpr int kChunk = 128;                      // frames per CTA
 constexpr int kWinPad = 416;                     // window zero-padded so that r + 16 j <= 207 stays in range
 constexpr int kSubSamples = (kSlots - 1) * kHop + kWinPad;   // 2816 = 11 * 256
-constexpr int kMelWeights = 512;                 // >= 501 non-zeros
+constexpr int kMelWeights = 768;                 // 501 non-zeros, every filter padded to a multiple of 4
 constexpr float kMelFloor = 1.192092955078125e-07f;
 constexpr int kStageLead = 4;                    // staging keeps 4 samples before the sub-tile (x[-1] and 16-byte alignment)
 constexpr int kStage = kSubSamples + kStageLead; // 2820 floats
 constexpr int kSlotFloats = 1024;                // one slot's exchange area (16 x 16 complex doubles) in floats
-constexpr int kPRowSkew = 1;                     // power spectrum of frame f starts f floats into its slot: banks (f + k) % 32
+// power spectrum of frame f starts p_skew(f) floats into its slot: the 16 rows fall on distinct banks for
+// the lane <-> frame reads of the mel stage, and the two slots of a warp are 16 banks apart for the stores
+__host__ __device__ constexpr int p_skew(int f) { return (f >> 1) + 16 * (f & 1); }
 constexpr int kOutRow = kSlotFloats + 17;        // staged log-mel row of frame f at 512 + 1041 f: banks (17 f + m) % 32
 
 struct KTables {
@@ -54,7 +56,7 @@ struct KTables {
     double2 tw[16 * 16];         // [k1][r]  = W256^(r k1)
     double2 post[16 * 16];       // [k2][k1] = W512^(k1 + 16 k2) = (cos, -sin)
     float   melw[kMelWeights];   // 0.25 * weights, packed per mel bin
-    int     melmeta[kMel];       // first | count << 9 | offset << 18
+    int     melmeta[kMel];       // first | (count / 4) << 9 | (offset / 4) << 16
 };
 
 struct Smem {
@@ -71,7 +73,7 @@ struct Smem {
     double  xb1[kSlots];         // x[160 f + 399]
     unsigned long long mbar;     // completion barrier of the bulk copy
 };
-static_assert(sizeof(Smem) <= 113 * 1024, "two CTAs per SM must fit in 228 KB");
+static_assert(sizeof(Smem) <= 114 * 1024 - 512, "two CTAs per SM must fit in 228 KB");
 static_assert(offsetof(Smem, stage) % 16 == 0 && offsetof(Smem, ex) % 16 == 0, "bulk-copy / vector alignment");
 
 struct cd { double re, im; };
@@ -129,6 +131,21 @@ __device__ __forceinline__ void dft16(const cd (&v)[16], cd (&o)[16]) {
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1)
         dft4(b[0][k1], b[1][k1], b[2][k1], b[3][k1], o[k1], o[k1 + 4], o[k1 + 8], o[k1 + 12]);
+}
+
+// ln(x) for normal positive x (the mel floor guarantees it): exponent + MUFU.LG2 of the mantissa.
+// |error| <= ~0.6 ulp of the result for results of magnitude 10..30 (the mantissa's log2 is in [0, 1), where
+// lg2.approx is accurate to 2^-22 absolute), i.e. as good as logf at a third of the instructions.
+__device__ __forceinline__ float ln_pos(float x) {
+    const int bits = __float_as_int(x);
+    const float e = (float)((bits >> 23) - 127);
+    const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+    float l2;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(l2) : "f"(m));
+    constexpr float ln2_hi = 0.693145751953125f;          // 16 significant bits: e * ln2_hi is exact
+    constexpr float ln2_lo = 1.42860682030941723212e-6f;
+    constexpr float ln2 = 0.69314718055994530942f;
+    return fmaf(e, ln2_hi, fmaf(l2, ln2, e * ln2_lo));
 }
 
 // ---- mbarrier + 1-D bulk copy (TMA) ---------------------------------------------------------
@@ -195,6 +212,7 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     // first sub-tile's PCM: issue the bulk copy before anything else
     if (tid == 0) {
         mbar_init(&sm.mbar, 1);
+        sm.stage[kStageLead - 1] = 0.0f;             // x[-1] of the clip's first sub-tile (later copies overwrite it)
         const StageRange sr = stage_range(t_begin * kHop, n, aligned);
         if (sr.hi > sr.lo) {
             mbar_expect_tx(&sm.mbar, (unsigned)(sr.hi - sr.lo) * 4u);
@@ -229,15 +247,32 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             if (kPeak) v = v / peak;                  // float32 division, like numpy's (R/processor.py:92)
             return v;
         };
+        const bool full = sr.hi == s0 + kSubSamples && (s0 == 0 || sr.lo == s0 - kStageLead);
+        if (full) {
+            // whole sub-tile staged and inside the clip: 4 samples per thread and step, no range checks
 #pragma unroll
-        for (int u = 0; u < kSubSamples / kThreads; ++u) {
-            const int i = tid + u * kThreads;
-            const double x = (double)sample(s0 + i);
-            const double xm = (double)sample(s0 + i - 1);
-            sm.dtile[i] = fma(-0.97, xm, x);
-            const int f = i / kHop, rem = i - f * kHop;
-            if (rem == 0 && f < kSlots) sm.xb0[f] = x;
-            if (rem == 79 && f >= 2) sm.xb1[f - 2] = x;          // 399 = 2 * 160 + 79
+            for (int u = 0; u < 3; ++u) {
+                const int q = tid + u * kThreads;
+                if (q < kSubSamples / 4) {
+                    float4 x4 = *reinterpret_cast<const float4*>(sm.stage + kStageLead + 4 * q);
+                    float xp = sm.stage[kStageLead - 1 + 4 * q];
+                    if (kPeak) { x4.x /= peak; x4.y /= peak; x4.z /= peak; x4.w /= peak; xp /= peak; }
+                    const double x0 = (double)x4.x, x1 = (double)x4.y, x2 = (double)x4.z, x3 = (double)x4.w;
+                    double2* d2 = reinterpret_cast<double2*>(sm.dtile + 4 * q);
+                    d2[0] = make_double2(fma(-0.97, (double)xp, x0), fma(-0.97, x0, x1));
+                    d2[1] = make_double2(fma(-0.97, x1, x2), fma(-0.97, x2, x3));
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < kSubSamples / kThreads; ++u) {
+                const int i = tid + u * kThreads;
+                sm.dtile[i] = fma(-0.97, (double)sample(s0 + i - 1), (double)sample(s0 + i));
+            }
+        }
+        if (tid < kSlots) {
+            sm.xb0[tid] = (double)sample(s0 + tid * kHop);
+            sm.xb1[tid] = (double)sample(s0 + tid * kHop + kFrame - 1);
         }
         __syncthreads();                            // dtile ready; staging and the exchange area are free again
 
@@ -301,13 +336,14 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         __syncwarp();                                // the slot's exchange area is now free for its power spectrum
 
         // ---- real split + power ----
-        float* P = exf + slot * (kSlotFloats + kPRowSkew);       // 256 floats, skewed by one float per slot
+        float* P = exf + slot * kSlotFloats + p_skew(slot);      // 256 floats inside the slot's own area
         const int partner = (lane & 16) | ((16 - r) & 15);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
             double pr = __shfl_sync(0xffffffffu, a[15 - k2].re, partner);
             double pi = __shfl_sync(0xffffffffu, a[15 - k2].im, partner);
-            if (r == 0) { pr = a[(16 - k2) & 15].re; pi = a[(16 - k2) & 15].im; }
+            pr = r == 0 ? a[(16 - k2) & 15].re : pr;             // thread 0 pairs Z[16 k2] with its own Z[256 - 16 k2]
+            pi = r == 0 ? a[(16 - k2) & 15].im : pi;
             const double2 w = sm.post[k2 * 16 + r];
             const double ar = a[k2].re, ai = a[k2].im;
             const double sr_ = ar + pr, dr = ar - pr, si = ai + pi, di = ai - pi;
@@ -320,22 +356,29 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
 
         // ---- sparse mel + ln: lane <-> frame (weights broadcast, power spectra conflict-free) ----
         {
-            const float* Pf = exf + mf * (kSlotFloats + kPRowSkew);
+            const float* Pf = exf + mf * kSlotFloats + p_skew(mf);
             float* orow = exf + 512 + mf * kOutRow;
-            const bool active = t0 + mf < t_end;
+            const double on = (t0 + mf < t_end) ? 1.0 : 0.0;
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
                 const int m = mg + 16 * i;
                 const int meta = sm.melmeta[m];
-                const int first = meta & 511, count = (meta >> 9) & 511, off = meta >> 18;
+                const int first = meta & 511, count4 = (meta >> 9) & 127, off4 = meta >> 16;
+                const float4* w4 = reinterpret_cast<const float4*>(sm.melw) + off4;
+                const float* pk = Pf + first;
                 float acc = 0.0f;
-                for (int q = 0; q < count; ++q) acc = fmaf(sm.melw[off + q], Pf[first + q], acc);
-                const float lg = logf(fmaxf(acc, kMelFloor));
-                orow[m] = lg;
-                if (active) {
-                    s1[i] += (double)lg;
-                    s2[i] = fma((double)lg, (double)lg, s2[i]);
+                for (int q = 0; q < count4; ++q) {
+                    const float4 w = w4[q];
+                    acc = fmaf(w.x, pk[4 * q + 0], acc);
+                    acc = fmaf(w.y, pk[4 * q + 1], acc);
+                    acc = fmaf(w.z, pk[4 * q + 2], acc);
+                    acc = fmaf(w.w, pk[4 * q + 3], acc);
                 }
+                const float lg = ln_pos(fmaxf(acc, kMelFloor));
+                orow[m] = lg;
+                const double lgd = (double)lg;
+                s1[i] = fma(on, lgd, s1[i]);
+                s2[i] = fma(on * lgd, lgd, s2[i]);
             }
         }
         __syncthreads();                            // staged rows complete
@@ -356,18 +399,19 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
 
     // ---- per-chunk statistics: ordered reduction over the 16 frame lanes ----
     __syncthreads();
-    double* red = reinterpret_cast<double*>(sm.ex);   // [2][16][80]
+    constexpr int kRedRow = kMel + 1;                  // odd stride: the 16 frame lanes hit distinct banks
+    double* red = reinterpret_cast<double*>(sm.ex);   // [2][16][81]
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
-        red[mf * kMel + mg + 16 * i] = s1[i];
-        red[kSlots * kMel + mf * kMel + mg + 16 * i] = s2[i];
+        red[mf * kRedRow + mg + 16 * i] = s1[i];
+        red[kSlots * kRedRow + mf * kRedRow + mg + 16 * i] = s2[i];
     }
     __syncthreads();
     if (tid < 2 * kMel) {
         const int which = tid / kMel, m = tid - which * kMel;
         double acc = 0.0;
 #pragma unroll
-        for (int sl = 0; sl < kSlots; ++sl) acc += red[which * kSlots * kMel + sl * kMel + m];
+        for (int sl = 0; sl < kSlots; ++sl) acc += red[which * kSlots * kRedRow + sl * kRedRow + m];
         partials[((size_t)b * chunks_per_clip + chunk) * (2 * kMel) + tid] = acc;
     }
 }
@@ -474,12 +518,12 @@ int get_tables(const KTables** out) {
                 double ang = -2.0 * M_PI * double(k1 + 16 * k2) / 512.0;
                 h.post[k2 * 16 + k1] = make_double2(std::cos(ang), std::sin(ang));
             }
-        MelCsr csr = build_mel_csr(k_mel(), STX_K_NFFT / 2 + 1, kMel, 0.25);
+        MelCsr csr = build_mel_csr(k_mel(), STX_K_NFFT / 2 + 1, kMel, 0.25, 4, 256);
         if (csr.weights.size() > size_t(kMelWeights)) { set_error("mel table overflow"); return STX_EINVAL; }
         for (int i = 0; i < kMelWeights; ++i) h.melw[i] = i < int(csr.weights.size()) ? csr.weights[i] : 0.0f;
         for (int m = 0; m < kMel; ++m) {
             if (csr.first[m] + csr.count[m] > 256) { set_error("mel filter %d reaches the Nyquist bin", m); return STX_EINVAL; }
-            h.melmeta[m] = csr.first[m] | (csr.count[m] << 9) | (csr.offset[m] << 18);
+            h.melmeta[m] = csr.first[m] | ((csr.count[m] / 4) << 9) | ((csr.offset[m] / 4) << 16);
         }
         KTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(KTables)));

@@ -151,7 +151,7 @@ const std::vector<double>& w_mel() {
     return fb;
 }
 
-MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double scale) {
+MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double scale, int pad, int limit) {
     MelCsr c;
     c.first.resize(nmel); c.count.resize(nmel); c.offset.resize(nmel);
     for (int m = 0; m < nmel; ++m) {
@@ -159,8 +159,16 @@ MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double 
         for (int k = 0; k < nbins; ++k)
             if (fb[size_t(k) * nmel + m] != 0.0) { if (lo < 0) lo = k; hi = k; }
         if (lo < 0) { lo = 0; hi = -1; }
-        c.first[m] = lo; c.count[m] = hi - lo + 1; c.offset[m] = int(c.weights.size());
-        for (int k = lo; k <= hi; ++k) c.weights.push_back(float(fb[size_t(k) * nmel + m] * scale));
+        int count = hi - lo + 1;
+        if (pad > 1) {
+            count = (count + pad - 1) / pad * pad;
+            if (count == 0) count = pad;
+            if (lo + count > limit) lo = limit - count;      // leading zeros instead of trailing ones
+            if (lo < 0) lo = 0;
+        }
+        c.first[m] = lo; c.count[m] = count; c.offset[m] = int(c.weights.size());
+        for (int k = lo; k < lo + count; ++k)
+            c.weights.push_back(k < nbins ? float(fb[size_t(k) * nmel + m] * scale) : 0.0f);
     }
     return c;
 }

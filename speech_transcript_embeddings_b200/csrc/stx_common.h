@@ -50,7 +50,9 @@ struct MelCsr {
     std::vector<int>   first, count, offset;
     std::vector<float> weights;
 };
-MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double scale);
+// `pad` > 1 pads every row to a multiple of `pad` weights (zeros) starting at a multiple of `pad` in
+// `weights`, and keeps first + count <= limit so that padded entries still index valid bins.
+MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double scale, int pad = 1, int limit = 1 << 30);
 
 int check_device();   // 0 if the current device is sm_100, else STX_EDEVICE
 
