@@ -111,7 +111,7 @@ def _cfg2_clips():
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return None
     procs = os.cpu_count() or 1
     pool = ReferencePool(args.recipe, procs, _cfg2_clips())
     for _ in range(args.warmup):
@@ -131,8 +131,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
-    return 0
+    return line
 
 
 # --------------------------------------------------------------------------------------------
@@ -398,6 +397,7 @@ def run_b200(args):
                         "sample": f"one pass over the {CLIPS_PER_BATCH} x {CLIP_SECONDS:.0f} s cfg2 batch, one clip per call "
                                   f"(R/processor.py:101-105), pool of {procs} processes; {secs:.2f} s"}
 
+    line = None
     if rank == 0:
         line = {
             "metric": "log-mel audio-seconds per second", "value": value, "unit": "audio-s/s", "n_gpus": world,
@@ -414,10 +414,25 @@ def run_b200(args):
                                                 "adds host packing into pinned memory; 1 rank, wall clock"}},
             "gpu_launches": launches_timed, "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line
+
+
+class _QuietStdout:
+    """Everything except the final JSON line goes to stderr, whatever libraries print (NCCL writes its
+    version banner to stdout at communicator creation)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -430,9 +445,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    with _QuietStdout():
+        line = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":

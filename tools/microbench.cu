@@ -109,6 +109,28 @@ __global__ void k_lds(float* out) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// shared loads with duplicated addresses: how many wavefronts does a table read cost when both
+// half-warps (or neighbouring lanes) read the same elements?  mode 0: idx = lane, 1: lane & 15, 2: lane >> 1
+template <typename V, int kMode>
+__global__ void k_lds_dup(float* out) {
+    __shared__ V buf[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = V{};
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int base = kMode == 0 ? lane : (kMode == 1 ? (lane & 15) : (lane >> 1));
+    float acc = 0;
+    int idx = base;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) {
+            V x = buf[(idx + i * 32) & 2047];
+            acc += *reinterpret_cast<float*>(&x);
+        }
+        idx += 32 * ILP;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 template <typename F>
 static float time_ms(F launch) {
     cudaEvent_t a, b;
@@ -148,6 +170,13 @@ int main() {
     report("LDS.32", time_ms([&] { k_lds<float><<<blocks, threads>>>((float*)out); }), 1);
     report("LDS.64", time_ms([&] { k_lds<float2><<<blocks, threads>>>((float*)out); }), 1);
     report("LDS.128", time_ms([&] { k_lds<float4><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.128 idx=lane", time_ms([&] { k_lds_dup<float4, 0><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.128 idx=lane&15", time_ms([&] { k_lds_dup<float4, 1><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.128 idx=lane>>1", time_ms([&] { k_lds_dup<float4, 2><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.64 idx=lane", time_ms([&] { k_lds_dup<float2, 0><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.64 idx=lane&15", time_ms([&] { k_lds_dup<float2, 1><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.64 idx=lane>>1", time_ms([&] { k_lds_dup<float2, 2><<<blocks, threads>>>((float*)out); }), 1);
+    report("LDS.32 idx=lane&15", time_ms([&] { k_lds_dup<float, 1><<<blocks, threads>>>((float*)out); }), 1);
     CHECK(cudaDeviceSynchronize());
     CHECK(cudaGetLastError());
     return 0;
