@@ -12,20 +12,36 @@
 // reference's own rounding points (complex64 spectrum, float32 log-mel).
 //
 // Three kernels:
-//   k_frames    one CTA per (clip, chunk of 128 frames): PCM -> raw log-mel (written in place into the
+//   k_frames    one CTA per (clip, chunk of frames): PCM -> raw log-mel (written in place into the
 //               output tensor, whose [T_pad/2,160] rows are exactly [T_pad,80] rows) + per-chunk
 //               per-bin (sum, sum of squares) partials in float64
 //   k_finalize  one CTA per clip: ordered reduction of the partials -> mean, 1/sqrt(var_ddof1 + 1e-7)
 //   k_normalize in-place CMVN, padding rows, attention mask
 //
-// Frame pipeline (16 threads per frame, 16 frames in flight per CTA):
-//   y[i] = w[i] * (d[i] - c),  d[i] = x[i] - 0.97 x[i-1],  c = 0.03 * mean(frame)      (w[0] = w[399] = 0)
-//   z[n] = y[2n] + j y[2n+1]  (n < 200, zero to 256)  -> 256-point complex FFT as 16 x 16:
-//     pass 1  thread r:  16-point DFT over z[r + 16 j] (j >= 13 are zero), times W256^(r k1) -> smem
-//     pass 2  thread k1: 16-point DFT over r -> Z[k1 + 16 k2]
-//   real split  2 X[k] = (Z[k] + conj Z[256-k]) - j W512^k (Z[k] - conj Z[256-k])   (partner by shuffle)
-//   power (after rounding X to float32, like the reference's complex64) -> sparse mel -> ln
+// k_frames keeps ONE FRAME PER LANE: a tile is 32 consecutive frames of a clip and the 16 warps of the
+// CTA split each frame's 512-point real FFT (n = 16 n1 + n2, k = k1 + 32 k2) between them, so every
+// per-warp quantity that is not data (window, twiddles, mel weights) is warp-uniform and comes from the
+// constant bank or a shared-memory broadcast, and every shared-memory access is lane-contiguous
+// (conflict-free by construction):
+//
+//   stage    one cp.async.bulk (TMA 1-D bulk copy) per tile lands the tile's 5364 raw samples in shared memory
+//            on an mbarrier while the previous tile is transformed (clips that are not 16-byte aligned, and the
+//            <= 3 tail samples of a clip, are read with plain loads)
+//   convert  every sample is converted to float64 ONCE: d[i] = x[i] - 0.97 x[i-1] (the pre-emphasis of every
+//            frame at once; the frame mean enters after the FFT), stored in rows of 161 doubles (odd stride:
+//            lane f reads row f + const without bank conflicts)
+//   pass 1   warp n2: y[n1] = W[i] d[i], i = 16 n1 + n2 (W = 2^15 * Povey), real DFT-32 over n1 in
+//            registers (codelets.cuh, generated), times W512^(n2 k1) -> shared [k1][n2][lane]
+//   pass 2   warp k1: complex DFT-16 over n2 -> X[k1 + 32 k2] (k2 >= 8 are the mirrored bins 512 - k, same power);
+//            warp 0 does the two real rows k1 = 0 and k1 = 16
+//   DC       the reference subtracts the frame mean m before pre-emphasis; with c = 0.03 m that is
+//            y - c W, i.e. X - c * FFT(W) by linearity: 2 FMAs per bin with a constant table;
+//            400 c = sum(d) - 0.97 (x[399] - x[-1]) from a two-level sum of the per-warp sums of d
+//   power    |X|^2 in float64, rounded to float32 -> shared [bin][lane]
+//   mel      warp w: mel bins w, w + 16, ...: filters padded to a fixed length per slot (no loop, no
+//            metadata decode) -> ln -> staged rows -> coalesced stores + float64 sum / sum of squares per bin
 #include "stx_common.h"
+#include "codelets.cuh"
 #include <cmath>
 #include <cstddef>
 #include <mutex>
@@ -36,102 +52,64 @@ namespace {
 constexpr int kFrame = STX_K_FRAME;
 constexpr int kHop = STX_K_HOP;
 constexpr int kMel = STX_K_NMEL;
-constexpr int kSlots = 16;                       // frames in flight per CTA
-constexpr int kThreads = kSlots * 16;            // 256
-constexpr int kChunk = 128;                      // frames per CTA
-constexpr int kWinPad = 416;                     // window zero-padded so that r + 16 j <= 207 stays in range
-constexpr int kSubSamples = (kSlots - 1) * kHop + kWinPad;   // 2816 = 11 * 256
-constexpr int kMelWeights = 768;                 // 501 non-zeros, every filter padded to a multiple of 4
+constexpr int kTile = 32;                        // frames per tile = lanes
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;            // 512
+constexpr int kTileSamples = (kTile - 1) * kHop + kFrame;   // 5360
+constexpr int kLead = 4;                         // the staged range starts 4 samples early (x[-1], 16-byte alignment)
+constexpr int kStage = kLead + kTileSamples + 4; // 5368 floats: stage[q] = x[160 t0 - 4 + q]
+constexpr int kDRow = kHop + 1;                  // d rows: 160 doubles + 1 pad
+constexpr int kDBuf = 34 * kDRow;                // 33.5 hops per tile
+constexpr int kMinChunk = 64;                    // smallest chunk of frames per CTA (sizes the partials workspace)
 constexpr float kMelFloor = 1.192092955078125e-07f;
-constexpr int kStageLead = 4;                    // staging keeps 4 samples before the sub-tile (x[-1] and 16-byte alignment)
-constexpr int kStage = kSubSamples + kStageLead; // 2820 floats
-constexpr int kSlotFloats = 1024;                // one slot's exchange area (16 x 16 complex doubles) in floats
-// power spectrum of frame f starts p_skew(f) floats into its slot: the 16 rows fall on distinct banks for
-// the lane <-> frame reads of the mel stage, and the two slots of a warp are 16 banks apart for the stores
-__host__ __device__ constexpr int p_skew(int f) { return (f >> 1) + 16 * (f & 1); }
-constexpr int kOutRow = kSlotFloats + 17;        // staged log-mel row of frame f at 512 + 1041 f: banks (17 f + m) % 32
+constexpr int kOutRow = kMel + 1;                // staged log-mel rows: odd stride, lane <-> row is conflict-free
+constexpr int kStatThreads = 6 * kMel;           // 480 threads store 6 rows of 80 bins per step
+// Statistics are accumulated in FIXED POINT (int64), so they do not depend on how a clip is cut into chunks,
+// tiles or row groups: a clip's features are bit-identical whatever batch it is in.  Adding 1.5 * 2^(52 - s) to
+// a double rounds it to a multiple of 2^-s and leaves that integer in the low mantissa bits.  x is a float32
+// with |x| < 2^7 (a natural log), so x is exact on the 2^-32 grid down to |x| = 2^-9 and x^2 (exact in
+// float64) is split into a multiple of 2^-20 plus a remainder below 2^-21 kept on the 2^-56 grid; 2^24 frames
+// per clip fit in 63 bits.  (A single 2^-28 grid for x^2 is not enough: a 2-frame clip has variances ~1e-7.)
+constexpr double kFix1 = 1.5 * 1048576.0;        // 1.5 * 2^20: grid 2^-32 (sum x)
+constexpr double kFixH = 1.5 * 4294967296.0;     // 1.5 * 2^32: grid 2^-20 (sum x^2, high part)
+constexpr double kFixL = 1.5 * 0.0625;           // 1.5 * 2^-4: grid 2^-56 (sum x^2, low part)
+constexpr int kStatWords = 3 * kMel;             // per chunk: sum x | sum x^2 high | sum x^2 low
+// mel slot i holds bins 16 i .. 16 i + 15 (one per warp), every filter of a slot padded to the same length
+__host__ __device__ constexpr int mel_len(int slot) { return slot == 0 ? 4 : slot == 1 ? 4 : slot == 2 ? 8 : slot == 3 ? 12 : 16; }
+__host__ __device__ constexpr int mel_off(int slot) { return slot == 0 ? 0 : mel_off(slot - 1) + 16 * mel_len(slot - 1); }
+constexpr int kMelWeights = mel_off(5);          // 704
+
+// warp-uniform tables (constant bank)
+__constant__ double  c_win[16][25];              // [n2][n1] = W[16 n1 + n2], W = 2^15 * Povey
+__constant__ double2 c_tw[16][16];               // [n2][k1] = W512^(n2 k1)
+__constant__ double2 c_wh[16][16];               // [k1][k2] = FFT512(W)[k1 + 32 k2]; row 0: [k2] = bin 32 k2 (k2 = 1..7), [8 + k2] = bin 16 + 32 k2
 
 struct KTables {
-    double  win[kWinPad];        // 2^15 * Povey, zero beyond 400
-    double2 tw[16 * 16];         // [k1][r]  = W256^(r k1)
-    double2 post[16 * 16];       // [k2][k1] = W512^(k1 + 16 k2) = (cos, -sin)
-    float   melw[kMelWeights];   // 0.25 * weights, packed per mel bin
-    int     melmeta[kMel];       // first | (count / 4) << 9 | (offset / 4) << 16
+    float melw[kMelWeights];     // [slot][warp][mel_len(slot)]
+    int   melfirst[kMel];        // first FFT bin of the padded filter of mel bin m
 };
 
 struct Smem {
-    double  dtile[kSubSamples];  // d[i] = x[i] - 0.97 x[i-1] of the current sub-tile (float64)
-    double  win[kWinPad];
-    double2 tw[256];
-    double2 post[256];
-    double2 ex[kSlots * 256];    // 16 x 16 exchange per slot (XOR-swizzled); later aliased by the power
-                                 // spectra, the staged log-mel rows and the statistics reduction
-    float   stage[kStage + 12];  // raw PCM of the NEXT sub-tile, landed by cp.async.bulk (TMA) while this one computes
+    double2 ex[15][16][kTile];   // pass-1 output rows k1 = 1..15: [k1 - 1][n2][lane]; later aliased by the staged
+                                 // log-mel rows and the statistics reduction
+    double  ex0[16][kTile];      // row k1 = 0  (real)
+    double  ex16[16][kTile];     // row k1 = 16 (real)
+    union {
+        double d[kDBuf];         // pre-emphasised samples of the tile (float64), rows of 161
+        float  P[256][kTile];    // power spectrum [bin][lane] (pass 2 onwards); row 0 is zeroed every tile
+    } u;
+    float   stage[kStage];       // raw PCM of the next tile, landed by cp.async.bulk
+    double  psum[kTile][17];     // per-warp sums of d, [lane][n2]
+    double  cval[kTile];         // 0.03 * mean of each frame
+    double  xb[kTile];           // 0.97 (x[399] - x[-1]) of each frame
     float   melw[kMelWeights];
-    int     melmeta[kMel];
-    double  xb0[kSlots];         // x[160 f]       of each frame of the sub-tile
-    double  xb1[kSlots];         // x[160 f + 399]
+    int     melfirst[kMel];
     unsigned long long mbar;     // completion barrier of the bulk copy
+    unsigned long long cbar;     // "all 32 values of cval are written" (one arrival per warp)
 };
-static_assert(sizeof(Smem) <= 114 * 1024 - 512, "two CTAs per SM must fit in 228 KB");
-static_assert(offsetof(Smem, stage) % 16 == 0 && offsetof(Smem, ex) % 16 == 0, "bulk-copy / vector alignment");
-
-struct cd { double re, im; };
-__device__ __forceinline__ cd operator+(cd a, cd b) { return {a.re + b.re, a.im + b.im}; }
-__device__ __forceinline__ cd operator-(cd a, cd b) { return {a.re - b.re, a.im - b.im}; }
-__device__ __forceinline__ cd cmul(cd a, double wr, double wi) {
-    return {fma(a.re, wr, -(a.im * wi)), fma(a.re, wi, a.im * wr)};
-}
-
-// forward 4-point DFT (W4 = -j)
-__device__ __forceinline__ void dft4(cd a0, cd a1, cd a2, cd a3, cd& A0, cd& A1, cd& A2, cd& A3) {
-    cd t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = a1 - a3;
-    A0 = t0 + t2;
-    A2 = t0 - t2;
-    A1 = {t1.re + t3.im, t1.im - t3.re};
-    A3 = {t1.re - t3.im, t1.im + t3.re};
-}
-// same with a3 == 0
-__device__ __forceinline__ void dft4_3(cd a0, cd a1, cd a2, cd& A0, cd& A1, cd& A2, cd& A3) {
-    cd t0 = a0 + a2, t1 = a0 - a2;
-    A0 = t0 + a1;
-    A2 = t0 - a1;
-    A1 = {t1.re + a1.im, t1.im - a1.re};
-    A3 = {t1.re - a1.im, t1.im + a1.re};
-}
-
-// forward 16-point DFT, natural order in and out: n = q + 4 m, k = k1 + 4 k2.
-// kPruned: inputs 13, 14, 15 are zero (and not read).
-template <bool kPruned>
-__device__ __forceinline__ void dft16(const cd (&v)[16], cd (&o)[16]) {
-    constexpr double c8 = 0.92387953251128675613;   // cos(pi/8)
-    constexpr double s8 = 0.38268343236508977173;   // sin(pi/8)
-    constexpr double h = 0.70710678118654752440;
-    cd b[4][4];
-    dft4(v[0], v[4], v[8], v[12], b[0][0], b[0][1], b[0][2], b[0][3]);
-    if (kPruned) {
-        dft4_3(v[1], v[5], v[9], b[1][0], b[1][1], b[1][2], b[1][3]);
-        dft4_3(v[2], v[6], v[10], b[2][0], b[2][1], b[2][2], b[2][3]);
-        dft4_3(v[3], v[7], v[11], b[3][0], b[3][1], b[3][2], b[3][3]);
-    } else {
-        dft4(v[1], v[5], v[9], v[13], b[1][0], b[1][1], b[1][2], b[1][3]);
-        dft4(v[2], v[6], v[10], v[14], b[2][0], b[2][1], b[2][2], b[2][3]);
-        dft4(v[3], v[7], v[11], v[15], b[3][0], b[3][1], b[3][2], b[3][3]);
-    }
-    // W16^(q k1)
-    b[1][1] = cmul(b[1][1], c8, -s8);                                            // W16^1
-    b[1][2] = {(b[1][2].re + b[1][2].im) * h, (b[1][2].im - b[1][2].re) * h};    // W16^2
-    b[1][3] = cmul(b[1][3], s8, -c8);                                            // W16^3
-    b[2][1] = {(b[2][1].re + b[2][1].im) * h, (b[2][1].im - b[2][1].re) * h};    // W16^2
-    b[2][2] = {b[2][2].im, -b[2][2].re};                                         // W16^4 = -j
-    b[2][3] = {(b[2][3].im - b[2][3].re) * h, -(b[2][3].re + b[2][3].im) * h};   // W16^6
-    b[3][1] = cmul(b[3][1], s8, -c8);                                            // W16^3
-    b[3][2] = {(b[3][2].im - b[3][2].re) * h, -(b[3][2].re + b[3][2].im) * h};   // W16^6
-    b[3][3] = cmul(b[3][3], -c8, s8);                                            // W16^9
-#pragma unroll
-    for (int k1 = 0; k1 < 4; ++k1)
-        dft4(b[0][k1], b[1][k1], b[2][k1], b[3][k1], o[k1], o[k1 + 4], o[k1 + 8], o[k1 + 12]);
-}
+static_assert(sizeof(Smem) <= 227 * 1024, "one CTA per SM must fit in 227 KB");
+static_assert(offsetof(Smem, stage) % 16 == 0, "bulk-copy destination alignment");
+static_assert(kTile * kOutRow * sizeof(float) <= sizeof(double2) * 15 * 16 * kTile, "staged rows alias the exchange area");
 
 // ln(x) for normal positive x (the mel floor guarantees it): exponent + MUFU.LG2 of the mantissa.
 // |error| <= ~0.6 ulp of the result for results of magnitude 10..30 (the mantissa's log2 is in [0, 1), where
@@ -171,24 +149,42 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Samples [lo, hi) of the clip that the bulk copy stages for the sub-tile starting at sample s0
-// (stage[kStageLead + i] = x[s0 + i]).  Both ends are multiples of 4 samples so that the copy is
-// 16-byte aligned and sized; everything else (the <= 3 tail samples of a clip, or the whole range when
-// the clip is not 16-byte aligned in memory) is read with plain loads in the pre-pass.
+// Samples [lo, hi) of the clip that the bulk copy stages for the tile starting at sample s0
+// (stage[kLead + i] = x[s0 + i]).  Both ends are multiples of 4 samples so that the copy is 16-byte
+// aligned and sized; everything else (the <= 3 tail samples of a clip, or the whole range when the clip
+// is not 16-byte aligned in memory) is read with plain loads in the conversion pass.
 struct StageRange { int lo, hi; };
 __device__ __forceinline__ StageRange stage_range(int s0, int n, bool aligned) {
     StageRange r;
-    r.lo = max(s0 - kStageLead, 0);
-    r.hi = aligned ? min(s0 + kSubSamples, n & ~3) : r.lo;
+    r.lo = max(s0 - kLead, 0);
+    r.hi = aligned ? min(s0 + kTileSamples + 4, n & ~3) : r.lo;
     if (r.hi < r.lo) r.hi = r.lo;
     return r;
 }
 
+template <int kSlot>
+__device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const float* __restrict__ melw,
+                                          const int* __restrict__ melfirst, int warp) {
+    constexpr int L = mel_len(kSlot);
+    const float4* w4 = reinterpret_cast<const float4*>(melw + mel_off(kSlot) + warp * L);
+    const float* pk = Pl + melfirst[16 * kSlot + warp] * kTile;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+        const float4 w = w4[q];
+        acc0 = fmaf(w.x, pk[(4 * q + 0) * kTile], acc0);
+        acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
+        acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
+        acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
+    }
+    return ln_pos(fmaxf(acc0 + acc1, kMelFloor));
+}
+
 template <bool kPeak>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
-         const float* __restrict__ peaks, const KTables* __restrict__ tab, int T_pad, int chunks_per_clip,
-         float* __restrict__ out, double* __restrict__ partials) {
+         const float* __restrict__ peaks, const KTables* __restrict__ tab, int T_pad, int chunk_frames,
+         int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -196,240 +192,229 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     const int chunk = blockIdx.x;
     const int n = lengths[b];
     const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
-    const int t_begin = chunk * kChunk;
+    const int t_begin = chunk * chunk_frames;
     if (t_begin >= T) return;                       // uniform per CTA
-    const int t_end = min(T, t_begin + kChunk);
+    const int t_end = min(T, t_begin + chunk_frames);
     const float* clip = pcm + offsets[b];
     const bool aligned = (reinterpret_cast<unsigned long long>(clip) & 15ull) == 0;
     const float peak = kPeak ? peaks[b] : 1.0f;
     float* out_b = out + (size_t)b * T_pad * kMel;
 
     const int tid = threadIdx.x;
-    const int slot = tid >> 4;
-    const int r = tid & 15;
     const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform: table reads stay on the constant path
 
-    // first sub-tile's PCM: issue the bulk copy before anything else
+    // first tile's PCM: issue the bulk copy before anything else
     if (tid == 0) {
         mbar_init(&sm.mbar, 1);
-        sm.stage[kStageLead - 1] = 0.0f;             // x[-1] of the clip's first sub-tile (later copies overwrite it)
+        mbar_init(&sm.cbar, kWarps);
         const StageRange sr = stage_range(t_begin * kHop, n, aligned);
         if (sr.hi > sr.lo) {
             mbar_expect_tx(&sm.mbar, (unsigned)(sr.hi - sr.lo) * 4u);
-            bulk_g2s(sm.stage + (sr.lo - (t_begin * kHop - kStageLead)), clip + sr.lo, (unsigned)(sr.hi - sr.lo) * 4u, &sm.mbar);
+            bulk_g2s(sm.stage + (sr.lo - (t_begin * kHop - kLead)), clip + sr.lo, (unsigned)(sr.hi - sr.lo) * 4u, &sm.mbar);
         }
     }
-    // tables -> shared
-    for (int i = tid; i < kWinPad; i += kThreads) sm.win[i] = tab->win[i];
-    sm.tw[tid] = tab->tw[tid];
-    sm.post[tid] = tab->post[tid];
     for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
-    if (tid < kMel) sm.melmeta[tid] = tab->melmeta[tid];
+    if (tid < kMel) sm.melfirst[tid] = tab->melfirst[tid];
     __syncthreads();                                // mbarrier init + tables visible
 
-    // mel stage mapping: lane <-> frame, 16 groups of 5 mel bins (g, g + 16, ..., g + 64)
-    const int mf = tid & 15, mg = tid >> 4;
-    double s1[5], s2[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) s1[i] = s2[i] = 0.0;
-    float* exf = reinterpret_cast<float*>(sm.ex);
-    unsigned parity = 0;
+    float* outstage = reinterpret_cast<float*>(&sm.ex[0][0][0]);
+    unsigned long long s1 = 0, s2h = 0, s2l = 0;    // fixed-point statistics of bin tid % 80 over the rows tid / 80 + 6 i
+    const int sbin = tid % kMel, srow = tid / kMel;
+    unsigned parity = 0, cparity = 0;
 
-    for (int t0 = t_begin; t0 < t_end; t0 += kSlots) {
-        // ---- pre-pass: staged PCM -> d[i] = x[i] - 0.97 x[i-1] (float64) ----
+    for (int t0 = t_begin; t0 < t_end; t0 += kTile) {
+        // ---- convert: staged PCM -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161 ----
         const int s0 = t0 * kHop;
         const StageRange sr = stage_range(s0, n, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         auto sample = [&](int g) -> float {          // x[g] of this clip, 0 outside
             float v = 0.0f;
-            if (g >= sr.lo && g < sr.hi) v = sm.stage[g - s0 + kStageLead];
+            if (g >= sr.lo && g < sr.hi) v = sm.stage[g - s0 + kLead];
             else if (g >= 0 && g < n) v = __ldg(clip + g);
             if (kPeak) v = v / peak;                  // float32 division, like numpy's (R/processor.py:92)
             return v;
         };
-        const bool full = sr.hi == s0 + kSubSamples && (s0 == 0 || sr.lo == s0 - kStageLead);
-        if (full) {
-            // whole sub-tile staged and inside the clip: 4 samples per thread and step, no range checks
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-                const int q = tid + u * kThreads;
-                if (q < kSubSamples / 4) {
-                    float4 x4 = *reinterpret_cast<const float4*>(sm.stage + kStageLead + 4 * q);
-                    float xp = sm.stage[kStageLead - 1 + 4 * q];
-                    if (kPeak) { x4.x /= peak; x4.y /= peak; x4.z /= peak; x4.w /= peak; xp /= peak; }
-                    const double x0 = (double)x4.x, x1 = (double)x4.y, x2 = (double)x4.z, x3 = (double)x4.w;
-                    double2* d2 = reinterpret_cast<double2*>(sm.dtile + 4 * q);
-                    d2[0] = make_double2(fma(-0.97, (double)xp, x0), fma(-0.97, x0, x1));
-                    d2[1] = make_double2(fma(-0.97, x1, x2), fma(-0.97, x2, x3));
-                }
+        if (sr.lo == s0 - kLead && sr.hi == s0 + kTileSamples + 4) {
+            // whole tile staged and inside the clip: no range checks
+#pragma unroll 1
+            for (int i = tid; i < kTileSamples; i += kThreads) {
+                float xm = sm.stage[kLead - 1 + i], xi = sm.stage[kLead + i];
+                if (kPeak) { xm = xm / peak; xi = xi / peak; }
+                sm.u.d[i + (unsigned)i / kHop] = fma(-0.97, (double)xm, (double)xi);
+            }
+            if (tid < kTile) {
+                float xa = sm.stage[kLead + tid * kHop + kFrame - 1], xz = sm.stage[kLead - 1 + tid * kHop];
+                if (kPeak) { xa = xa / peak; xz = xz / peak; }
+                sm.xb[tid] = 0.97 * ((double)xa - (double)xz);
             }
         } else {
 #pragma unroll 1
-            for (int u = 0; u < kSubSamples / kThreads; ++u) {
-                const int i = tid + u * kThreads;
-                sm.dtile[i] = fma(-0.97, (double)sample(s0 + i - 1), (double)sample(s0 + i));
-            }
+            for (int i = tid; i < kTileSamples; i += kThreads)
+                sm.u.d[i + (unsigned)i / kHop] = fma(-0.97, (double)sample(s0 + i - 1), (double)sample(s0 + i));
+            if (tid < kTile)
+                sm.xb[tid] = 0.97 * ((double)sample(s0 + tid * kHop + kFrame - 1) - (double)sample(s0 + tid * kHop - 1));
         }
-        if (tid < kSlots) {
-            sm.xb0[tid] = (double)sample(s0 + tid * kHop);
-            sm.xb1[tid] = (double)sample(s0 + tid * kHop + kFrame - 1);
-        }
-        __syncthreads();                            // dtile ready; staging and the exchange area are free again
+        __syncthreads();                            // d ready; staging is free again
 
-        // next sub-tile's PCM lands while this one is transformed
-        if (tid == 0 && t0 + kSlots < t_end) {
-            const StageRange nx = stage_range(s0 + kSlots * kHop, n, aligned);
+        // next tile's PCM lands while this one is transformed
+        if (tid == 0 && t0 + kTile < t_end) {
+            const StageRange nx = stage_range(s0 + kTile * kHop, n, aligned);
             if (nx.hi > nx.lo) {
                 mbar_expect_tx(&sm.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
-                bulk_g2s(sm.stage + (nx.lo - (s0 + kSlots * kHop - kStageLead)), clip + nx.lo,
+                bulk_g2s(sm.stage + (nx.lo - (s0 + kTile * kHop - kLead)), clip + nx.lo,
                          (unsigned)(nx.hi - nx.lo) * 4u, &sm.mbar);
             }
         }
 
-        // ---- frame -> y (float64) ----
-        const double2* dfr = reinterpret_cast<const double2*>(sm.dtile + slot * kHop);
-        const double2* wfr = reinterpret_cast<const double2*>(sm.win);
-        cd v[16];
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            double2 p = dfr[r + 16 * j];
-            v[j] = {p.x, p.y};
-        }
-#pragma unroll
-        for (int j = 0; j < 12; ++j) s += v[j].re + v[j].im;
-        if (r == 0) s -= v[0].re;                    // i = 0 is not part of sum_{i=1..399} d[i]
-        if (r < 8) s += v[12].re + v[12].im;         // i = 2 (r + 192) (+1) <= 399  <=>  r <= 7
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        // 0.03 * sum(x) = sum_{i>=1} d[i] + x[0] - 0.97 x[399]
-        const double c = (s + sm.xb0[slot] - 0.97 * sm.xb1[slot]) * (1.0 / 400.0);
-#pragma unroll
-        for (int j = 0; j < 13; ++j) {
-            double2 w = wfr[r + 16 * j];
-            v[j].re = w.x * (v[j].re - c);
-            v[j].im = w.y * (v[j].im - c);
-        }
-
-        // ---- pass 1 ----  exchange element (row k1, column n2) lives at k1 * 16 + (n2 ^ (k1 & 7))
-        cd a[16];
-        dft16<true>(v, a);
-        double2* ex = sm.ex + slot * 256;
-        ex[r] = make_double2(a[0].re, a[0].im);
-#pragma unroll
-        for (int k1 = 1; k1 < 16; ++k1) {
-            double2 w = sm.tw[k1 * 16 + r];
-            cd m = cmul(a[k1], w.x, w.y);
-            ex[k1 * 16 + (r ^ (k1 & 7))] = make_double2(m.re, m.im);
-        }
-        __syncwarp();
-
-        // ---- pass 2 (thread r now owns row k1 = r) ----
-#pragma unroll
-        for (int n2 = 0; n2 < 16; ++n2) {
-            double2 p = ex[r * 16 + (n2 ^ (r & 7))];
-            v[n2] = {p.x, p.y};
-        }
-        dft16<false>(v, a);                          // a[k2] = Z[r + 16 k2]
-        __syncwarp();                                // the slot's exchange area is now free for its power spectrum
-
-        // ---- real split + power ----
-        float* P = exf + slot * kSlotFloats + p_skew(slot);      // 256 floats inside the slot's own area
-        const int partner = (lane & 16) | ((16 - r) & 15);
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) {
-            double pr = __shfl_sync(0xffffffffu, a[15 - k2].re, partner);
-            double pi = __shfl_sync(0xffffffffu, a[15 - k2].im, partner);
-            pr = r == 0 ? a[(16 - k2) & 15].re : pr;             // thread 0 pairs Z[16 k2] with its own Z[256 - 16 k2]
-            pi = r == 0 ? a[(16 - k2) & 15].im : pi;
-            const double2 w = sm.post[k2 * 16 + r];
-            const double ar = a[k2].re, ai = a[k2].im;
-            const double sr_ = ar + pr, dr = ar - pr, si = ai + pi, di = ai - pi;
-            const double xr = fma(w.y, dr, fma(w.x, si, sr_));      // 2 Re X[k]
-            const double xi = fma(w.y, si, fma(-w.x, dr, di));      // 2 Im X[k]
-            const float fr = (float)xr, fi = (float)xi;             // the reference rounds X to complex64
-            P[r + 16 * k2] = fmaf(fr, fr, fi * fi);                 // 4 |X|^2 (the 1/4 is in the mel weights)
-        }
-        __syncthreads();                            // all 16 power spectra visible
-
-        // ---- sparse mel + ln: lane <-> frame (weights broadcast, power spectra conflict-free) ----
+        // ---- window + pass 1 (warp = n2) ----
         {
-            const float* Pf = exf + mf * kSlotFloats + p_skew(mf);
-            float* orow = exf + 512 + mf * kOutRow;
-            const double on = (t0 + mf < t_end) ? 1.0 : 0.0;
+            const double* D = sm.u.d + kDRow * lane + warp;
+            double y[25];
+            double sa = 0.0, sb = 0.0;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int m = mg + 16 * i;
-                const int meta = sm.melmeta[m];
-                const int first = meta & 511, count4 = (meta >> 9) & 127, off4 = meta >> 16;
-                const float4* w4 = reinterpret_cast<const float4*>(sm.melw) + off4;
-                const float* pk = Pf + first;
-                float acc = 0.0f;
-                for (int q = 0; q < count4; ++q) {
-                    const float4 w = w4[q];
-                    acc = fmaf(w.x, pk[4 * q + 0], acc);
-                    acc = fmaf(w.y, pk[4 * q + 1], acc);
-                    acc = fmaf(w.z, pk[4 * q + 2], acc);
-                    acc = fmaf(w.w, pk[4 * q + 3], acc);
+            for (int n1 = 0; n1 < 25; ++n1) {
+                const double v = D[16 * n1 + (n1 >= 10) + (n1 >= 20)];
+                y[n1] = c_win[warp][n1] * v;
+                if (n1 & 1) sb += v; else sa += v;
+            }
+            sm.psum[lane][warp] = sa + sb;
+            double re[17], im[17];
+            codelets::k_pass1<double>(y, re, im);
+            sm.ex0[warp][lane] = re[0];
+            sm.ex16[warp][lane] = re[16];
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) {
+                const double2 t = *reinterpret_cast<const double2*>(&c_tw[warp][k1]);
+                sm.ex[k1 - 1][warp][lane] = make_double2(fma(re[k1], t.x, -(im[k1] * t.y)), fma(re[k1], t.y, im[k1] * t.x));
+            }
+        }
+        __syncthreads();                            // exchange complete; d is dead, its storage becomes the power spectrum
+
+        // ---- c = 0.03 * mean(frame): warp w sums the 16 partials of frames 2 w and 2 w + 1 ----
+        {
+            const int fr = 2 * warp + (lane >> 4), r = lane & 15;
+            double v = sm.psum[fr][r];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            if (r == 0) sm.cval[fr] = (v - sm.xb[fr]) * (1.0 / 400.0);
+            if (warp == 1) sm.u.P[0][lane] = 0.0f;   // padded mel filters may touch bin 0 with a zero weight
+            // c is only needed after the DFT-16 below: one arrival per warp on an mbarrier now, the wait is there,
+            // so that no warp idles here
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.cbar)) : "memory");
+        }
+
+        // ---- pass 2 (warp = k1), DC correction, power ----
+        {
+            double c = 0.0;
+            auto put = [&](int bin, double xr, double xi, double2 wh) {
+                const double a = fma(-c, wh.x, xr), bb = fma(-c, wh.y, xi);
+                sm.u.P[bin][lane] = (float)fma(a, a, bb * bb);
+            };
+            if (warp == 0) {
+                double a[16], r[16];
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) { a[n2] = sm.ex0[n2][lane]; r[n2] = sm.ex16[n2][lane]; }
+                double e0r[7], e0i[7], e16r[8], e16i[8];
+                codelets::k_pass2_edge<double>(a, r, e0r, e0i, e16r, e16i);
+                mbar_wait(&sm.cbar, cparity);
+                c = sm.cval[lane];
+#pragma unroll
+                for (int k2 = 1; k2 < 8; ++k2) put(32 * k2, e0r[k2 - 1], e0i[k2 - 1], c_wh[0][k2]);
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) put(16 + 32 * k2, e16r[k2], e16i[k2], c_wh[0][8 + k2]);
+            } else {
+                double xr[16], xi[16], yr[16], yi[16];
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) {
+                    const double2 v = sm.ex[warp - 1][n2][lane];
+                    xr[n2] = v.x; xi[n2] = v.y;
                 }
-                const float lg = ln_pos(fmaxf(acc, kMelFloor));
-                orow[m] = lg;
-                const double lgd = (double)lg;
-                s1[i] = fma(on, lgd, s1[i]);
-                s2[i] = fma(on * lgd, lgd, s2[i]);
+                codelets::dft16<double>(xr, xi, yr, yi);
+                mbar_wait(&sm.cbar, cparity);
+                c = sm.cval[lane];
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2)
+                    put(k2 < 8 ? warp + 32 * k2 : 512 - warp - 32 * k2, yr[k2], yi[k2], c_wh[warp][k2]);
             }
+            cparity ^= 1;
         }
-        __syncthreads();                            // staged rows complete
+        __syncthreads();
 
-        // ---- coalesced store of the sub-tile's rows: frames t0 .. are one contiguous block of out ----
+        // ---- sparse mel + ln (warp w: bins w, w + 16, ..., w + 64; weights are warp-uniform broadcasts) ----
         {
-            const int rows = min(min(t_end, T_pad) - t0, kSlots);
-            float* dst = out_b + (size_t)t0 * kMel;
-            for (int e = tid; e < rows * (kMel / 4); e += kThreads) {
-                const int f = e / (kMel / 4), m4 = (e - f * (kMel / 4)) * 4;
-                const float* src = exf + 512 + f * kOutRow + m4;
-                reinterpret_cast<float4*>(dst)[e] = make_float4(src[0], src[1], src[2], src[3]);
+            const float* Pl = &sm.u.P[0][lane];
+            float* orow = outstage + lane * kOutRow + warp;
+            orow[0]  = mel_slot<0>(Pl, sm.melw, sm.melfirst, warp);
+            orow[16] = mel_slot<1>(Pl, sm.melw, sm.melfirst, warp);
+            orow[32] = mel_slot<2>(Pl, sm.melw, sm.melfirst, warp);
+            orow[48] = mel_slot<3>(Pl, sm.melw, sm.melfirst, warp);
+            orow[64] = mel_slot<4>(Pl, sm.melw, sm.melfirst, warp);
+        }
+        __syncthreads();
+
+        // ---- coalesced store of the tile's rows (one contiguous block of out) + statistics ----
+        if (tid < kStatThreads) {
+            const int rows = min(t_end - t0, kTile);
+            const int keep = min(T_pad - t0, rows);           // frames >= T_pad count for the statistics but are not stored
+            float* dst = out_b + (size_t)t0 * kMel + tid;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const int row = srow + 6 * i;
+                if (row < rows) {
+                    const float v = outstage[row * kOutRow + sbin];
+                    if (row < keep) dst[i * kStatThreads] = v;
+                    const double vd = (double)v;
+                    const double sq = vd * vd, hi = sq + kFixH, lo = sq - (hi - kFixH);      // all exact
+                    s1 += (unsigned long long)__double_as_longlong(vd + kFix1) - (unsigned long long)__double_as_longlong(kFix1);
+                    s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
+                    s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
+                }
             }
         }
-        // the next iteration's pre-pass only touches dtile / xb / stage; its __syncthreads orders these
-        // reads of the exchange area before the next pass 1 overwrites it
+        // the next iteration's conversion pass only touches d / xb / stage; its __syncthreads orders these
+        // reads of the staged rows before pass 1 overwrites the exchange area, and the mel stage's reads of the
+        // power spectrum (aliased with d) are all before the __syncthreads above
     }
 
-    // ---- per-chunk statistics: ordered reduction over the 16 frame lanes ----
+    // ---- per-chunk statistics: ordered reduction over the 6 row groups ----
     __syncthreads();
-    constexpr int kRedRow = kMel + 1;                  // odd stride: the 16 frame lanes hit distinct banks
-    double* red = reinterpret_cast<double*>(sm.ex);   // [2][16][81]
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-        red[mf * kRedRow + mg + 16 * i] = s1[i];
-        red[kSlots * kRedRow + mf * kRedRow + mg + 16 * i] = s2[i];
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(&sm.ex[0][0][0]);     // [3][6][80]
+    if (tid < kStatThreads) {
+        red[tid] = s1;
+        red[kStatThreads + tid] = s2h;
+        red[2 * kStatThreads + tid] = s2l;
     }
     __syncthreads();
-    if (tid < 2 * kMel) {
+    if (tid < kStatWords) {
         const int which = tid / kMel, m = tid - which * kMel;
-        double acc = 0.0;
+        unsigned long long acc = 0;
 #pragma unroll
-        for (int sl = 0; sl < kSlots; ++sl) acc += red[which * kSlots * kRedRow + sl * kRedRow + m];
-        partials[((size_t)b * chunks_per_clip + chunk) * (2 * kMel) + tid] = acc;
+        for (int g = 0; g < 6; ++g) acc += red[which * kStatThreads + g * kMel + m];
+        partials[((size_t)b * chunks_per_clip + chunk) * kStatWords + tid] = (long long)acc;
     }
 }
 
 // mean and 1/sqrt(var + 1e-7) per (clip, bin); var with ddof = 1 (…seamless_m4t.py:257-262)
-__global__ void k_finalize(const int* __restrict__ lengths, const double* __restrict__ partials,
+__global__ void k_finalize(const int* __restrict__ lengths, const long long* __restrict__ partials, int chunk_frames,
                            int chunks_per_clip, double* __restrict__ stats) {
     const int b = blockIdx.x, m = threadIdx.x;
     if (m >= kMel) return;
     const int n = lengths[b];
     const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
-    const int nchunks = (T + kChunk - 1) / kChunk;
-    double a1 = 0.0, a2 = 0.0;
+    const int nchunks = (T + chunk_frames - 1) / chunk_frames;
+    long long i1 = 0, i2h = 0, i2l = 0;                            // exact: integer sums are order-independent
     for (int c = 0; c < nchunks; ++c) {
-        const double* p = partials + ((size_t)b * chunks_per_clip + c) * (2 * kMel);
-        a1 += p[m];
-        a2 += p[kMel + m];
+        const long long* p = partials + ((size_t)b * chunks_per_clip + c) * kStatWords;
+        i1 += p[m];
+        i2h += p[kMel + m];
+        i2l += p[2 * kMel + m];
     }
+    const double a1 = (double)i1 * (1.0 / 4294967296.0);
+    const double a2 = (double)i2h * (1.0 / 1048576.0) + (double)i2l * (1.0 / 72057594037927936.0);
     const double mean = a1 / (double)T;
     // a single frame has no ddof=1 variance: numpy returns NaN there and so do we
     double var = T > 1 ? (a2 - a1 * mean) / (double)(T - 1) : __longlong_as_double(0x7ff8000000000000LL);
@@ -505,25 +490,46 @@ int get_tables(const KTables** out) {
     if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return STX_EINVAL; }
     std::lock_guard<std::mutex> lock(g_tab_mutex);
     if (!g_tab[dev]) {
-        static KTables h;   // ~13 KB, filled once
+        static KTables h;
         const std::vector<double>& w = k_window();
-        for (int i = 0; i < kWinPad; ++i) h.win[i] = i < kFrame ? w[i] * 32768.0 : 0.0;
-        for (int k1 = 0; k1 < 16; ++k1)
-            for (int r = 0; r < 16; ++r) {
-                double ang = -2.0 * M_PI * double(r * k1) / 256.0;
-                h.tw[k1 * 16 + r] = make_double2(std::cos(ang), std::sin(ang));
+        // constant-bank tables; FFT512 of the scaled window by direct summation in long double
+        static double win[16][25];
+        static double2 tw[16][16], wh[16][16];
+        for (int n2 = 0; n2 < 16; ++n2)
+            for (int n1 = 0; n1 < 25; ++n1) {
+                win[n2][n1] = w[16 * n1 + n2] * 32768.0;
             }
-        for (int k2 = 0; k2 < 16; ++k2)
+        for (int n2 = 0; n2 < 16; ++n2)
             for (int k1 = 0; k1 < 16; ++k1) {
-                double ang = -2.0 * M_PI * double(k1 + 16 * k2) / 512.0;
-                h.post[k2 * 16 + k1] = make_double2(std::cos(ang), std::sin(ang));
+                const double ang = -2.0 * M_PI * double(n2 * k1) / 512.0;
+                tw[n2][k1] = make_double2(std::cos(ang), std::sin(ang));
             }
-        MelCsr csr = build_mel_csr(k_mel(), STX_K_NFFT / 2 + 1, kMel, 0.25, 4, 256);
-        if (csr.weights.size() > size_t(kMelWeights)) { set_error("mel table overflow"); return STX_EINVAL; }
-        for (int i = 0; i < kMelWeights; ++i) h.melw[i] = i < int(csr.weights.size()) ? csr.weights[i] : 0.0f;
+        auto what = [&](int k) {
+            long double re = 0.0L, im = 0.0L;
+            for (int i = 0; i < kFrame; ++i) {
+                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)((i * k) % 512) / 512.0L;
+                re += (long double)(w[i] * 32768.0) * cosl(ang);
+                im += (long double)(w[i] * 32768.0) * sinl(ang);
+            }
+            return make_double2((double)re, (double)im);
+        };
+        for (int k1 = 0; k1 < 16; ++k1)
+            for (int k2 = 0; k2 < 16; ++k2) wh[k1][k2] = what(k1 + 32 * k2);
+        for (int k2 = 0; k2 < 8; ++k2) wh[0][8 + k2] = what(16 + 32 * k2);     // row 0: bins 32 k2 and 16 + 32 k2
+        STX_CUDA(cudaMemcpyToSymbol(c_win, win, sizeof(win)));
+        STX_CUDA(cudaMemcpyToSymbol(c_tw, tw, sizeof(tw)));
+        STX_CUDA(cudaMemcpyToSymbol(c_wh, wh, sizeof(wh)));
+        // mel filters, padded per slot to mel_len(slot) weights ending at or before bin 255
+        const std::vector<double>& fb = k_mel();
         for (int m = 0; m < kMel; ++m) {
-            if (csr.first[m] + csr.count[m] > 256) { set_error("mel filter %d reaches the Nyquist bin", m); return STX_EINVAL; }
-            h.melmeta[m] = csr.first[m] | ((csr.count[m] / 4) << 9) | ((csr.offset[m] / 4) << 16);
+            const int slot = m / 16, wrp = m % 16, L = mel_len(slot);
+            int lo = -1, hi = -1;
+            for (int k = 0; k <= STX_K_NFFT / 2; ++k)
+                if (fb[size_t(k) * kMel + m] != 0.0) { if (lo < 0) lo = k; hi = k; }
+            if (lo < 0 || hi - lo + 1 > L || hi > 255) { set_error("mel filter %d does not fit its slot", m); return STX_EINVAL; }
+            if (lo + L > 256) lo = 256 - L;
+            h.melfirst[m] = lo;
+            for (int q = 0; q < L; ++q) h.melw[mel_off(slot) + wrp * L + q] = float(fb[size_t(lo + q) * kMel + m]);
         }
         KTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(KTables)));
@@ -537,6 +543,20 @@ int get_tables(const KTables** out) {
 }
 
 inline int frames_of(int n) { return n >= kFrame ? 1 + (n - kFrame) / kHop : 0; }
+
+// Frames per CTA (a multiple of the 32-frame tile): with one CTA per SM the grid runs in waves of `sms` CTAs, so
+// pick the chunk that minimises waves * tiles-per-chunk for B clips of max_frames; ties go to the larger chunk
+// (fewer prologues).  Lengths live on the device, so ragged batches are sized by their longest clip.
+inline int pick_chunk(int B, int max_frames, int sms) {
+    int best = kMinChunk;
+    long long best_cost = -1;
+    for (int chunk = kMinChunk; chunk <= 512; chunk += kTile) {
+        const long long ctas = (long long)B * ((max_frames + chunk - 1) / chunk);
+        const long long cost = ((ctas + sms - 1) / sms) * (chunk / kTile);
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = chunk; }
+    }
+    return best;
+}
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 }  // namespace
@@ -547,8 +567,8 @@ extern "C" {
 int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     using namespace stx;
     if (B < 0 || max_length < 0 || !bytes) { set_error("stx_fbank_k_workspace: bad argument"); return STX_EINVAL; }
-    const int chunks = (frames_of(max_length) + kChunk - 1) / kChunk;
-    *bytes = align256(size_t(B) * std::max(chunks, 1) * 2 * kMel * sizeof(double)) +
+    const int chunks = (frames_of(max_length) + kMinChunk - 1) / kMinChunk;
+    *bytes = align256(size_t(B) * std::max(chunks, 1) * kStatWords * sizeof(long long)) +
              align256(size_t(B) * kMel * 2 * sizeof(double));
     return 0;
 }
@@ -569,22 +589,31 @@ int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_l
     if (int rc = get_tables(&tab)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    const int chunks = std::max((frames_of(max_length) + kChunk - 1) / kChunk, 1);
-    double* partials = static_cast<double*>(d_ws);
+    const int max_frames = frames_of(max_length);
+    const int ws_chunks = std::max((max_frames + kMinChunk - 1) / kMinChunk, 1);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        STX_CUDA(cudaGetDevice(&dev));
+        STX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int chunk_frames = pick_chunk(B, max_frames, sms);
+    const int chunks = std::max((max_frames + chunk_frames - 1) / chunk_frames, 1);
+    long long* partials = static_cast<long long*>(d_ws);
     double* stats = reinterpret_cast<double*>(static_cast<char*>(d_ws) +
-                                              align256(size_t(B) * chunks * 2 * kMel * sizeof(double)));
+                                              align256(size_t(B) * ws_chunks * kStatWords * sizeof(long long)));
     if (frames_of(max_length) > 0) {
         if (d_peak) {
             STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
-                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad, chunks,
-                       d_out, partials);
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
+                       chunk_frames, chunks, d_out, partials);
         } else {
             STX_LAUNCH(k_frames<false>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
-                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad, chunks,
-                       d_out, partials);
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
+                       chunk_frames, chunks, d_out, partials);
         }
     }
-    STX_LAUNCH(k_finalize, dim3(B), dim3(96), 0, st, d_lengths, partials, chunks, stats);
+    STX_LAUNCH(k_finalize, dim3(B), dim3(96), 0, st, d_lengths, partials, chunk_frames, chunks, stats);
     const int quads = T_pad * (kMel / 4);
     const int gx = std::max(1, std::min((quads + 255) / 256, 64));
     STX_LAUNCH(k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, stats, T_pad, padding_value, normalize,
