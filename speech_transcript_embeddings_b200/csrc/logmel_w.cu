@@ -8,14 +8,26 @@
 //
 // The reference's default path is float32 (torch.stft); this kernel is float32 throughout.
 //
-//   w_frames    one CTA per (clip, chunk of 128 frames); 8 threads per frame in pass 1
-//               z[n] = y[2n] + j y[2n+1], n < 200; 200-point complex FFT as 25 x 8:
-//                 pass 1  thread n2 (8 per frame): radix-25 (5 x 5) over z[n2 + 8 n1], times W200^(n2 k1)
-//                 pass 2  100 rows (4 frames x 25) per warp: 8-point DFT over n2 -> Z[k1 + 25 k2]
-//               real split (pairs k, 200-k), power, sparse mel, log10 -> out (raw) + per-clip max (atomic)
+//   w_frames    one CTA per (clip, chunk of frames), ONE FRAME PER LANE like k_frames (fbank_k.cu): a tile is 32
+//               consecutive frames and the 16 warps split each frame's 400-point real FFT
+//               (n = 16 n1 + n2, k = k1 + 25 k2):
+//                 stage    cp.async.bulk (TMA) of the tile's raw samples, one tile ahead
+//                 layout   reflect / zero padding and the peak divisor applied once per sample, rows of 161 floats
+//                 pass 1   warp n2: Hann window, real DFT-25 over n1 in registers (codelets.cuh), times W400^(n2 k1)
+//                 pass 2   warp k1 = 1..12: complex DFT-16 over n2 -> X[k1 + 25 k2] (k >= 201 are the mirrored bins);
+//                          warp 0: the real row k1 = 0
+//                 power -> shared [bin][lane]; mel (fixed-length padded filters) -> log10 -> coalesced stores
+//                 along t, per-clip max by warp reduce + integer atomics
 //   w_finish    in-place max(x, max - 8), (x + 4) / 4 and the mask
+//
+// DFT engine: a shared-memory / register FFT on the FP32 pipe.  The alternative the task names, DFT-as-GEMM on
+// tcgen05 with split operands, needs 2 * 400 * 402 flop per frame and pass (x3 passes for float32-grade accuracy:
+// 185 GFLOP for the 192 000 frames of the 64 x 30 s batch, >= 130 us at the measured 1.4 PFLOP/s), against
+// ~7.3 kflop per frame for the FFT; see DESIGN.md §5.
 #include "stx_common.h"
+#include "codelets.cuh"
 #include <cmath>
+#include <cstddef>
 #include <mutex>
 
 namespace stx {
@@ -25,111 +37,87 @@ constexpr int kN = STX_W_NFFT;          // 400
 constexpr int kHop = STX_W_HOP;         // 160
 constexpr int kMel = STX_W_NMEL;        // 80
 constexpr int kBins = kN / 2 + 1;       // 201
-constexpr int kThreads = 256;
-constexpr int kRound = 32;              // frames in flight per CTA (4 per warp)
-constexpr int kChunk = 128;             // frames per CTA
-constexpr int kTile = (kRound - 1) * kHop + kN;   // 5360 samples
-constexpr int kExRow = 9;               // padded row of 8 complex
-constexpr int kExFrame = 232;           // complex per frame in the exchange (25 * 9 = 225, padded: 1856 B = 64 mod 128)
-constexpr int kPRow = 203;              // odd stride for the power spectrum rows
-constexpr int kMelWeights = 400;        // >= 391 non-zeros
+constexpr int kTile = 32;               // frames per tile = lanes
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;   // 512
+constexpr int kTileSamples = (kTile - 1) * kHop + kN;   // 5360
+constexpr int kXRow = kHop + 1;         // padded rows: odd stride, lane f reads row f + const without bank conflicts
+constexpr int kXBuf = 34 * kXRow;
+__host__ __device__ constexpr int mel_len(int slot) { return slot < 3 ? 4 : slot == 3 ? 8 : 16; }
+__host__ __device__ constexpr int mel_off(int slot) { return slot == 0 ? 0 : mel_off(slot - 1) + 16 * mel_len(slot - 1); }
+constexpr int kMelWeights = mel_off(5);  // 576
+
+__constant__ float  cw_win[16][25];     // [n2][n1] = hann[16 n1 + n2]
+__constant__ float2 cw_tw[16][16];      // [n2][k1] = W400^(n2 k1), k1 = 0..12
 
 struct WTables {
-    float  win[kN];
-    float2 tw[25 * 8];          // [k1][n2] = W200^(n2 k1)
-    float2 post[104];           // W400^k, k = 0..100
-    float  melw[kMelWeights];   // 0.25 * weights
-    int    melmeta[kMel];       // first | count << 9 | offset << 18
+    float melw[kMelWeights];            // [slot][warp][mel_len(slot)]
+    int   melfirst[kMel];
 };
 
 struct Smem {
-    float  pcm[kTile];
-    float  win[kN];
-    float2 tw[200];
-    float2 post[104];
+    float2 ex[12][16][kTile];           // pass-1 rows k1 = 1..12: [k1 - 1][n2][lane]
+    float  ex0[16][kTile];              // row k1 = 0 (real)
+    float  P[kBins][kTile];             // power spectrum [bin][lane]
+    float  xs[kXBuf + 2];               // padded, windowable samples of the tile (+2: keeps `stage` 16-byte aligned)
+    float  stage[kTileSamples];         // raw PCM of the next tile (cp.async.bulk)
     float  melw[kMelWeights];
-    int    melmeta[kMel];
-    float2 ex[kRound * kExFrame];
-    float  P[kRound * kPRow];
-    float  wmax[kThreads / 32];
+    int    melfirst[kMel];
+    float  wmax[kWarps];
+    unsigned long long mbar;
 };
-static_assert(sizeof(Smem) <= 112 * 1024, "two CTAs per SM must fit");
+static_assert(sizeof(Smem) <= 227 * 1024, "shared memory");
+static_assert(offsetof(Smem, stage) % 16 == 0, "bulk-copy destination alignment");
 
-struct cf { float re, im; };
-__device__ __forceinline__ cf operator+(cf a, cf b) { return {a.re + b.re, a.im + b.im}; }
-__device__ __forceinline__ cf operator-(cf a, cf b) { return {a.re - b.re, a.im - b.im}; }
-__device__ __forceinline__ cf cmul(cf a, float wr, float wi) {
-    return {fmaf(a.re, wr, -(a.im * wi)), fmaf(a.re, wi, a.im * wr)};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ cf cfma(float s, cf a, cf b) { return {fmaf(s, a.re, b.re), fmaf(s, a.im, b.im)}; }
-
-// forward 5-point DFT
-__device__ __forceinline__ void dft5(cf a0, cf a1, cf a2, cf a3, cf a4, cf& A0, cf& A1, cf& A2, cf& A3, cf& A4) {
-    constexpr float c1 = 0.30901699437494742410f;    // cos(2 pi / 5)
-    constexpr float c2 = -0.80901699437494742410f;   // cos(4 pi / 5)
-    constexpr float s1 = 0.95105651629515357212f;    // sin(2 pi / 5)
-    constexpr float s2 = 0.58778525229247312917f;    // sin(4 pi / 5)
-    cf t1 = a1 + a4, t2 = a2 + a3, t3 = a1 - a4, t4 = a2 - a3;
-    A0 = a0 + t1 + t2;
-    cf m1 = cfma(c2, t2, cfma(c1, t1, a0));
-    cf m2 = cfma(c1, t2, cfma(c2, t1, a0));
-    cf n1 = {fmaf(s2, t4.re, s1 * t3.re), fmaf(s2, t4.im, s1 * t3.im)};
-    cf n2 = {fmaf(-s1, t4.re, s2 * t3.re), fmaf(-s1, t4.im, s2 * t3.im)};
-    A1 = {m1.re + n1.im, m1.im - n1.re};
-    A4 = {m1.re - n1.im, m1.im + n1.re};
-    A2 = {m2.re + n2.im, m2.im - n2.re};
-    A3 = {m2.re - n2.im, m2.im + n2.re};
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// W25^e = (cos(2 pi e / 25), -sin(2 pi e / 25)) for the exponents q * k1 that occur (q, k1 in 1..4);
-// e is a compile-time constant after unrolling, so the switch folds away
-__device__ __forceinline__ cf tw25(cf a, int e) {
-    switch (e) {
-        case 1: return cmul(a, 0.96858316112863107605f, -0.24868988716485479484f);
-        case 2: return cmul(a, 0.87630668004386358394f, -0.48175367410171532345f);
-        case 3: return cmul(a, 0.72896862742141155245f, -0.68454710592868861507f);
-        case 4: return cmul(a, 0.53582679497899654564f, -0.84432792550201507531f);
-        case 6: return cmul(a, 0.06279051952931352654f, -0.99802672842827155897f);
-        case 8: return cmul(a, -0.42577929156507271502f, -0.90482705246601946580f);
-        case 9: return cmul(a, -0.63742398974868974548f, -0.77051324277578925326f);
-        case 12: return cmul(a, -0.99211470131447776488f, -0.12533323356430453588f);
-        default: return cmul(a, -0.63742398974868952344f, 0.77051324277578936428f);   // 16
+// Clip samples [lo, hi) that the bulk copy stages for the tile whose first padded sample is g0 = 160 t0 - 200
+// (stage[g - g0] = x[g]); multiples of 4 samples; the rest (reflected / tail samples, unaligned clips) are plain loads.
+struct StageRange { int lo, hi; };
+__device__ __forceinline__ StageRange stage_range(int g0, int len, bool aligned) {
+    StageRange r;
+    r.lo = max(g0, 0);
+    r.hi = aligned ? min(g0 + kTileSamples, len & ~3) : r.lo;
+    if (r.hi < r.lo) r.hi = r.lo;
+    return r;
+}
+
+template <int kSlot>
+__device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const float* __restrict__ melw,
+                                          const int* __restrict__ melfirst, int warp) {
+    constexpr int L = mel_len(kSlot);
+    const float4* w4 = reinterpret_cast<const float4*>(melw + mel_off(kSlot) + warp * L);
+    const float* pk = Pl + melfirst[16 * kSlot + warp] * kTile;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+        const float4 w = w4[q];
+        acc0 = fmaf(w.x, pk[(4 * q + 0) * kTile], acc0);
+        acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
+        acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
+        acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
     }
-}
-
-// forward 25-point DFT, natural order: n = q + 5 m, k = k1 + 5 k2
-__device__ __forceinline__ void dft25(const cf (&v)[25], cf (&o)[25]) {
-    cf b[5][5];
-#pragma unroll
-    for (int q = 0; q < 5; ++q)
-        dft5(v[q], v[q + 5], v[q + 10], v[q + 15], v[q + 20], b[q][0], b[q][1], b[q][2], b[q][3], b[q][4]);
-#pragma unroll
-    for (int q = 1; q < 5; ++q)
-#pragma unroll
-        for (int k1 = 1; k1 < 5; ++k1) b[q][k1] = tw25(b[q][k1], q * k1);
-#pragma unroll
-    for (int k1 = 0; k1 < 5; ++k1)
-        dft5(b[0][k1], b[1][k1], b[2][k1], b[3][k1], b[4][k1], o[k1], o[k1 + 5], o[k1 + 10], o[k1 + 15], o[k1 + 20]);
-}
-
-// forward 8-point DFT, natural order
-__device__ __forceinline__ void dft8(const cf (&v)[8], cf (&o)[8]) {
-    constexpr float h = 0.70710678118654752440f;
-    // n = q + 2 m (q = 0, 1; m = 0..3), k = k1 + 4 k2
-    cf e0 = v[0] + v[4], e1 = v[0] - v[4], e2 = v[2] + v[6], e3 = v[2] - v[6];
-    cf E0 = e0 + e2, E2 = e0 - e2;
-    cf E1 = {e1.re + e3.im, e1.im - e3.re}, E3 = {e1.re - e3.im, e1.im + e3.re};
-    cf f0 = v[1] + v[5], f1 = v[1] - v[5], f2 = v[3] + v[7], f3 = v[3] - v[7];
-    cf F0 = f0 + f2, F2 = f0 - f2;
-    cf F1 = {f1.re + f3.im, f1.im - f3.re}, F3 = {f1.re - f3.im, f1.im + f3.re};
-    // W8^k1 on the odd half
-    cf G1 = {(F1.re + F1.im) * h, (F1.im - F1.re) * h};
-    cf G2 = {F2.im, -F2.re};
-    cf G3 = {(F3.im - F3.re) * h, -(F3.re + F3.im) * h};
-    o[0] = E0 + F0; o[4] = E0 - F0;
-    o[1] = E1 + G1; o[5] = E1 - G1;
-    o[2] = E2 + G2; o[6] = E2 - G2;
-    o[3] = E3 + G3; o[7] = E3 - G3;
+    return log10f(fmaxf(acc0 + acc1, 1e-10f));
 }
 
 // float max through integer atomics (works for any sign, destination initialised to -inf)
@@ -143,134 +131,137 @@ __global__ void w_init_max(float* __restrict__ clip_max, int B) {
     if (i < B) clip_max[i] = __int_as_float(0xff800000);
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
-         const float* __restrict__ peaks, const WTables* __restrict__ tab, int n_samples, float* __restrict__ out,
-         float* __restrict__ clip_max) {
+         const float* __restrict__ peaks, const WTables* __restrict__ tab, int n_samples, int chunk_frames,
+         float* __restrict__ out, float* __restrict__ clip_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int b = blockIdx.y;
     const int T = n_samples / kHop;
-    const int t_begin = blockIdx.x * kChunk;
+    const int t_begin = blockIdx.x * chunk_frames;
     if (t_begin >= T) return;
-    const int t_end = min(T, t_begin + kChunk);
+    const int t_end = min(T, t_begin + chunk_frames);
     const int len = min(lengths[b], n_samples);
     const float* clip = pcm + offsets[b];
+    const bool aligned = (reinterpret_cast<unsigned long long>(clip) & 15ull) == 0;
     const float peak = peaks ? peaks[b] : 1.0f;
     float* out_b = out + (size_t)b * kMel * T;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-    for (int i = tid; i < kN; i += kThreads) sm.win[i] = tab->win[i];
-    if (tid < 200) sm.tw[tid] = tab->tw[tid];
-    if (tid < 104) sm.post[tid] = tab->post[tid];
+    if (tid == 0) {
+        mbar_init(&sm.mbar, 1);
+        const int g0 = t_begin * kHop - kN / 2;
+        const StageRange sr = stage_range(g0, len, aligned);
+        if (sr.hi > sr.lo) {
+            mbar_expect_tx(&sm.mbar, (unsigned)(sr.hi - sr.lo) * 4u);
+            bulk_g2s(sm.stage + (sr.lo - g0), clip + sr.lo, (unsigned)(sr.hi - sr.lo) * 4u, &sm.mbar);
+        }
+    }
     for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
-    if (tid < kMel) sm.melmeta[tid] = tab->melmeta[tid];
+    if (tid < kMel) sm.melfirst[tid] = tab->melfirst[tid];
+    __syncthreads();
 
     float run_max = __int_as_float(0xff800000);
+    unsigned parity = 0;
 
-    for (int t0 = t_begin; t0 < t_end; t0 += kRound) {
-        __syncthreads();
-        // ---- PCM tile with zero padding to n_samples and reflect padding of 200 around it ----
+    for (int t0 = t_begin; t0 < t_end; t0 += kTile) {
+        // ---- layout: zero padding to n_samples, reflect padding of 200 around it, peak divisor; rows of 161 ----
         const int g0 = t0 * kHop - kN / 2;
-        for (int i = tid; i < kTile; i += kThreads) {
-            int g = g0 + i;
-            if (g < 0) g = -g;
-            if (g >= n_samples) g = 2 * (n_samples - 1) - g;
-            float x = (g >= 0 && g < len) ? __ldg(clip + g) : 0.0f;
-            if (peak != 1.0f) x = x / peak;          // float32 division, like numpy's (R/processor.py:92)
-            sm.pcm[i] = x;
+        const StageRange sr = stage_range(g0, len, aligned);
+        if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
+        if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {
+#pragma unroll 1
+            for (int i = tid; i < kTileSamples; i += kThreads) {
+                float x = sm.stage[i];
+                if (peak != 1.0f) x = x / peak;                // float32 division, like numpy's (R/processor.py:92)
+                sm.xs[i + (unsigned)i / kHop] = x;
+            }
+        } else {
+#pragma unroll 1
+            for (int i = tid; i < kTileSamples; i += kThreads) {
+                int g = g0 + i;
+                if (g < 0) g = -g;
+                if (g >= n_samples) g = 2 * (n_samples - 1) - g;
+                float x = 0.0f;
+                if (g >= sr.lo && g < sr.hi) x = sm.stage[g - g0];
+                else if (g >= 0 && g < len) x = __ldg(clip + g);
+                if (peak != 1.0f) x = x / peak;
+                sm.xs[i + (unsigned)i / kHop] = x;
+            }
+        }
+        __syncthreads();                            // xs ready; staging is free; the previous tile's mel stage is done with P
+
+        if (tid == 0 && t0 + kTile < t_end) {
+            const StageRange nx = stage_range(g0 + kTile * kHop, len, aligned);
+            if (nx.hi > nx.lo) {
+                mbar_expect_tx(&sm.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
+                bulk_g2s(sm.stage + (nx.lo - (g0 + kTile * kHop)), clip + nx.lo, (unsigned)(nx.hi - nx.lo) * 4u, &sm.mbar);
+            }
+        }
+
+        // ---- window + pass 1 (warp = n2) ----
+        {
+            const float* X = sm.xs + kXRow * lane + warp;
+            float y[25], re[13], im[13];
+#pragma unroll
+            for (int n1 = 0; n1 < 25; ++n1) y[n1] = cw_win[warp][n1] * X[16 * n1 + (n1 >= 10) + (n1 >= 20)];
+            codelets::w_pass1<float>(y, re, im);
+            sm.ex0[warp][lane] = re[0];
+#pragma unroll
+            for (int k1 = 1; k1 < 13; ++k1) {
+                const float2 t = cw_tw[warp][k1];
+                sm.ex[k1 - 1][warp][lane] = make_float2(fmaf(re[k1], t.x, -(im[k1] * t.y)), fmaf(re[k1], t.y, im[k1] * t.x));
+            }
         }
         __syncthreads();
 
-        // ---- pass 1: 8 threads per frame, 4 frames per warp ----
-        {
-            const int fw = lane >> 3, n2 = lane & 7;
-            const int fr = warp * 4 + fw;
-            const float2* x2 = reinterpret_cast<const float2*>(sm.pcm + fr * kHop);
-            const float2* w2 = reinterpret_cast<const float2*>(sm.win);
-            cf v[25], a[25];
+        // ---- pass 2 (warp = k1 <= 12) + power ----
+        if (warp == 0) {
+            float a[16], er[9], ei[9];
 #pragma unroll
-            for (int n1 = 0; n1 < 25; ++n1) {
-                const float2 x = x2[n2 + 8 * n1], w = w2[n2 + 8 * n1];
-                v[n1] = {x.x * w.x, x.y * w.y};
+            for (int n2 = 0; n2 < 16; ++n2) a[n2] = sm.ex0[n2][lane];
+            codelets::w_pass2_edge<float>(a, er, ei);
+#pragma unroll
+            for (int k2 = 0; k2 < 9; ++k2) sm.P[25 * k2][lane] = fmaf(er[k2], er[k2], ei[k2] * ei[k2]);
+        } else if (warp < 13) {
+            float xr[16], xi[16], yr[16], yi[16];
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const float2 v = sm.ex[warp - 1][n2][lane];
+                xr[n2] = v.x; xi[n2] = v.y;
             }
-            dft25(v, a);
-            float2* ex = sm.ex + fr * kExFrame;
-            ex[n2] = make_float2(a[0].re, a[0].im);
+            codelets::dft16<float>(xr, xi, yr, yi);
 #pragma unroll
-            for (int k1 = 1; k1 < 25; ++k1) {
-                const float2 w = sm.tw[k1 * 8 + n2];
-                const cf m = cmul(a[k1], w.x, w.y);
-                ex[k1 * kExRow + n2] = make_float2(m.re, m.im);
-            }
-        }
-        __syncwarp();
-
-        // ---- pass 2: the warp's 100 rows (frame, k1), 8-point DFT each ----
-        cf zz[4][8];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int row = lane + 32 * it;
-            if (row < 100) {
-                const int fw = row / 25, k1 = row - fw * 25;
-                const float2* ex = sm.ex + (warp * 4 + fw) * kExFrame + k1 * kExRow;
-                cf v[8];
-#pragma unroll
-                for (int n2 = 0; n2 < 8; ++n2) { const float2 p = ex[n2]; v[n2] = {p.x, p.y}; }
-                dft8(v, zz[it]);
-            }
-        }
-        __syncwarp();
-        // natural order Z[k1 + 25 k2] back into the frame's exchange area
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int row = lane + 32 * it;
-            if (row < 100) {
-                const int fw = row / 25, k1 = row - fw * 25;
-                float2* z = sm.ex + (warp * 4 + fw) * kExFrame;
-#pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) z[k1 + 25 * k2] = make_float2(zz[it][k2].re, zz[it][k2].im);
-            }
-        }
-        __syncwarp();
-
-        // ---- real split + power: pairs (k, 200 - k), k = 0..100, of the warp's 4 frames ----
-        for (int item = lane; item < 4 * 101; item += 32) {
-            const int fw = item / 101, k = item - fw * 101;
-            const int fr = warp * 4 + fw;
-            const float2* z = sm.ex + fr * kExFrame;
-            const float2 zk = z[k], zp = z[k == 0 ? 0 : 200 - k];
-            const float2 w = sm.post[k];
-            const float sr = zk.x + zp.x, dr = zk.x - zp.x, si = zk.y + zp.y, di = zk.y - zp.y;
-            const float u = fmaf(w.y, dr, w.x * si);
-            const float vv = fmaf(w.y, si, -(w.x * dr));
-            const float xr = sr + u, xi = di + vv;       // 2 X[k]
-            const float yr = sr - u, yi = vv - di;       // 2 X[200 - k]
-            float* P = sm.P + fr * kPRow;
-            P[k] = fmaf(xr, xr, xi * xi);
-            P[200 - k] = fmaf(yr, yr, yi * yi);
+            for (int k2 = 0; k2 < 16; ++k2)
+                sm.P[k2 < 8 ? warp + 25 * k2 : 400 - warp - 25 * k2][lane] = fmaf(yr[k2], yr[k2], yi[k2] * yi[k2]);
         }
         __syncthreads();
 
-        // ---- sparse mel + log10; lane <-> frame so that stores along t coalesce ----
+        // ---- mel + log10: lane <-> frame, so the stores along t coalesce ----
         {
+            const float* Pl = &sm.P[0][lane];
             const int t = t0 + lane;
-            const float* P = sm.P + lane * kPRow;
-#pragma unroll 2
-            for (int m = warp; m < kMel; m += kThreads / 32) {
-                const int meta = sm.melmeta[m];
-                const int first = meta & 511, count = (meta >> 9) & 511, off = meta >> 18;
-                float acc = 0.0f;
-                for (int q = 0; q < count; ++q) acc = fmaf(sm.melw[off + q], P[first + q], acc);
-                const float lg = log10f(fmaxf(acc, 1e-10f));
-                if (t < t_end) {
-                    out_b[(size_t)m * T + t] = lg;
-                    run_max = fmaxf(run_max, lg);
+            float v[5];
+            v[0] = mel_slot<0>(Pl, sm.melw, sm.melfirst, warp);
+            v[1] = mel_slot<1>(Pl, sm.melw, sm.melfirst, warp);
+            v[2] = mel_slot<2>(Pl, sm.melw, sm.melfirst, warp);
+            v[3] = mel_slot<3>(Pl, sm.melw, sm.melfirst, warp);
+            v[4] = mel_slot<4>(Pl, sm.melw, sm.melfirst, warp);
+            if (t < t_end) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    out_b[(size_t)(warp + 16 * i) * T + t] = v[i];
+                    run_max = fmaxf(run_max, v[i]);
                 }
             }
         }
+        // the next iteration's layout pass writes xs / reads stage only; its __syncthreads orders this mel stage's
+        // reads of P before the next pass 2 overwrites it
     }
 
 #pragma unroll
@@ -280,7 +271,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     if (tid == 0) {
         float m = sm.wmax[0];
 #pragma unroll
-        for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, sm.wmax[w]);
+        for (int w = 1; w < kWarps; ++w) m = fmaxf(m, sm.wmax[w]);
         atomic_max_float(clip_max + b, m);
     }
 }
@@ -327,20 +318,28 @@ int get_tables(const WTables** out) {
     if (!g_tab[dev]) {
         static WTables h;
         const std::vector<double>& w = w_window();
-        for (int i = 0; i < kN; ++i) h.win[i] = (float)w[i];
-        for (int k1 = 0; k1 < 25; ++k1)
-            for (int n2 = 0; n2 < 8; ++n2) {
-                double ang = -2.0 * M_PI * double(n2 * k1) / 200.0;
-                h.tw[k1 * 8 + n2] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        static float win[16][25];
+        static float2 tw[16][16];
+        for (int n2 = 0; n2 < 16; ++n2)
+            for (int n1 = 0; n1 < 25; ++n1) win[n2][n1] = (float)w[16 * n1 + n2];
+        for (int n2 = 0; n2 < 16; ++n2)
+            for (int k1 = 0; k1 < 16; ++k1) {
+                const double ang = -2.0 * M_PI * double((n2 * k1) % 400) / 400.0;
+                tw[n2][k1] = make_float2((float)std::cos(ang), (float)std::sin(ang));
             }
-        for (int k = 0; k < 104; ++k) {
-            double ang = -2.0 * M_PI * double(k) / 400.0;
-            h.post[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        STX_CUDA(cudaMemcpyToSymbol(cw_win, win, sizeof(win)));
+        STX_CUDA(cudaMemcpyToSymbol(cw_tw, tw, sizeof(tw)));
+        const std::vector<double>& fb = w_mel();
+        for (int m = 0; m < kMel; ++m) {
+            const int slot = m / 16, wrp = m % 16, L = mel_len(slot);
+            int lo = -1, hi = -1;
+            for (int k = 0; k < kBins; ++k)
+                if (fb[size_t(k) * kMel + m] != 0.0) { if (lo < 0) lo = k; hi = k; }
+            if (lo < 0 || hi - lo + 1 > L) { set_error("mel filter %d does not fit its slot", m); return STX_EINVAL; }
+            if (lo + L > kBins) lo = kBins - L;
+            h.melfirst[m] = lo;
+            for (int q = 0; q < L; ++q) h.melw[mel_off(slot) + wrp * L + q] = float(fb[size_t(lo + q) * kMel + m]);
         }
-        MelCsr csr = build_mel_csr(w_mel(), kBins, kMel, 0.25);
-        if (csr.weights.size() > size_t(kMelWeights)) { set_error("mel table overflow"); return STX_EINVAL; }
-        for (int i = 0; i < kMelWeights; ++i) h.melw[i] = i < int(csr.weights.size()) ? csr.weights[i] : 0.0f;
-        for (int m = 0; m < kMel; ++m) h.melmeta[m] = csr.first[m] | (csr.count[m] << 9) | (csr.offset[m] << 18);
         WTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(WTables)));
         STX_CUDA(cudaMemcpy(d, &h, sizeof(WTables), cudaMemcpyHostToDevice));
@@ -349,6 +348,18 @@ int get_tables(const WTables** out) {
     }
     *out = g_tab[dev];
     return 0;
+}
+
+// Frames per CTA (a multiple of the 32-frame tile), chosen like fbank_k.cu's pick_chunk: minimise waves x tiles.
+inline int pick_chunk(int B, int frames, int sms) {
+    int best = 64;
+    long long best_cost = -1;
+    for (int chunk = 64; chunk <= 512; chunk += kTile) {
+        const long long ctas = (long long)B * ((frames + chunk - 1) / chunk);
+        const long long cost = ((ctas + sms - 1) / sms) * (chunk / kTile);
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = chunk; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -383,8 +394,16 @@ int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_
     float* clip_max = static_cast<float*>(d_ws);
     const int T = n_samples / kHop;
     STX_LAUNCH(w_init_max, dim3((B + 255) / 256), dim3(256), 0, st, clip_max, B);
-    STX_LAUNCH(w_frames, dim3((T + kChunk - 1) / kChunk, B), dim3(kThreads), sizeof(Smem), st,
-               d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, n_samples, d_out, clip_max);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        STX_CUDA(cudaGetDevice(&dev));
+        STX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int chunk_frames = pick_chunk(B, T, sms);
+    STX_LAUNCH(w_frames, dim3((T + chunk_frames - 1) / chunk_frames, B), dim3(kThreads), sizeof(Smem), st,
+               d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, n_samples, chunk_frames,
+               d_out, clip_max);
     const size_t total = (size_t)kMel * T;
     const int gx = (int)std::max<size_t>(1, std::min<size_t>((total / 4 + 255) / 256, 64));
     STX_LAUNCH(w_finish, dim3(gx, B), dim3(256), 0, st, d_lengths, clip_max, n_samples, d_out, d_mask);

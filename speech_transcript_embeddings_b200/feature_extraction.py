@@ -12,7 +12,10 @@ exceptions.  One deliberate difference: ``return_tensors="pt"`` tensors live on 
 device (the reference moves them there right after the call, R/processor.py:118-121, so ``.to(device)``
 becomes a no-op); ``return_tensors="np"`` / ``None`` copies them back to host NumPy arrays.
 
-Host work here is only: pack the clips into one pinned buffer, one H2D copy, one C-ABI call.
+Host work here is only: pack the clips into one pinned buffer, H2D, C-ABI calls.  When the result is wanted on
+the host (``return_tensors="np"``, or ``output="host"`` for pinned CPU tensors like the reference's own CPU
+tensors) the batch is cut into chunks of clips and three streams overlap H2D(i+1) | kernels(i) | D2H(i-1), so
+the call costs about max(H2D, D2H) over PCIe instead of their sum.
 """
 from __future__ import annotations
 
@@ -140,6 +143,76 @@ class _B200ExtractorBase:
             raise StxError("this feature extractor needs a CUDA device (sm_100a); there is no CPU fallback")
         return self.device
 
+    # -- chunked three-stream pipeline (host in -> host out) -----------------------------------
+    CHUNK_BYTES = 12 << 20          # PCM bytes per chunk: large enough for PCIe efficiency, small enough to overlap
+
+    def _streams(self):
+        if getattr(self, "_pipe_streams", None) is None:
+            dev = self._device()
+            self._pipe_streams = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        return self._pipe_streams
+
+    @classmethod
+    def chunk_bounds(cls, offsets: np.ndarray, lengths: np.ndarray, chunk_bytes: int | None = None):
+        """Clip ranges [b0, b1) whose packed PCM is about ``chunk_bytes`` each (at least one clip per chunk)."""
+        chunk_bytes = cls.CHUNK_BYTES if chunk_bytes is None else chunk_bytes
+        B = int(lengths.size)
+        bounds, b0 = [], 0
+        while b0 < B:
+            b1 = b0 + 1
+            while b1 < B and (int(offsets[b1]) + int(lengths[b1]) - int(offsets[b0])) * 4 <= chunk_bytes:
+                b1 += 1
+            bounds.append((b0, b1))
+            b0 = b1
+        return bounds
+
+    def _pipeline(self, packed: "PackedClips", launch, outputs):
+        """Runs ``launch(pcm_chunk_d, offsets_d, lengths_d, b0, b1, max_len)`` per chunk of clips.
+
+        ``outputs`` = list of (device tensor [B, ...], pinned host tensor [B, ...]) pairs: rows b0:b1 are copied
+        back as soon as the chunk's kernels finish.  Returns after the last D2H copy has completed.
+        """
+        dev = self._device()
+        B = packed.batch_size
+        s_in, s_run, s_out = self._streams()
+        cur = torch.cuda.current_stream(dev)
+        for s_ in (s_in, s_run, s_out):
+            s_.wait_stream(cur)                                  # buffers allocated on the caller's stream are ready
+        bounds = self.chunk_bounds(packed.offsets, packed.lengths)
+        # chunk-relative offsets: every chunk is an independent call into the library
+        rel = packed.offsets.copy()
+        for b0, b1 in bounds:
+            rel[b0:b1] -= packed.offsets[b0]
+        meta = torch.empty(2 * B, dtype=torch.int64, pin_memory=True)
+        mv = meta.numpy()
+        mv[:B] = rel
+        mv[B:2 * B] = 0
+        mv[B:2 * B].view(np.int32)[:B] = packed.lengths
+        total = int(packed.offsets[-1]) + int(packed.lengths[-1]) if B else 0
+        pcm_d = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        meta_d = torch.empty(2 * B, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(s_in):
+            meta_d.copy_(meta, non_blocking=True)
+        off_d, len_d = meta_d[:B], meta_d[B:2 * B].view(torch.int32)[:B]
+        for b0, b1 in bounds:
+            lo = int(packed.offsets[b0])
+            hi = int(packed.offsets[b1 - 1]) + int(packed.lengths[b1 - 1])
+            with torch.cuda.stream(s_in):
+                pcm_d[lo:hi].copy_(packed.pcm[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in)
+                launch(pcm_d[lo:hi], off_d[b0:b1], len_d[b0:b1], b0, b1, int(packed.lengths[b0:b1].max()))
+                ev_run = torch.cuda.Event()
+                ev_run.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run)
+                for dev_t, host_t in outputs:
+                    host_t[b0:b1].copy_(dev_t[b0:b1], non_blocking=True)
+        s_out.synchronize()                                      # the caller holds the result on the host
+        cur.wait_stream(s_run)                                   # device buffers may be reused by the caller's stream
+
     # -- host -> device ----------------------------------------------------------------------
     def pack(self, clips: Sequence[np.ndarray]) -> PackedClips:
         """Copy clips into one pinned host buffer (reused across calls)."""
@@ -174,12 +247,20 @@ class _B200ExtractorBase:
         return pcm_d, offsets_d, lengths_d
 
     @staticmethod
-    def _finish(data: dict, return_tensors):
-        if return_tensors in ("pt", "torch"):
-            return BatchFeature(data)
-        if return_tensors in (None, "np", "numpy"):
-            return BatchFeature({k: v.cpu().numpy() for k, v in data.items()})
-        raise ValueError(f"return_tensors={return_tensors!r} is not supported (use 'pt' or 'np')")
+    def _check_return(return_tensors, output):
+        if return_tensors not in ("pt", "torch", None, "np", "numpy"):
+            raise ValueError(f"return_tensors={return_tensors!r} is not supported (use 'pt' or 'np')")
+        if output not in (None, "device", "host"):
+            raise ValueError("output must be 'device' or 'host'")
+        to_numpy = return_tensors in (None, "np", "numpy")
+        on_host = to_numpy or output == "host"
+        return to_numpy, on_host
+
+    @staticmethod
+    def _finish(data: dict, to_numpy: bool):
+        if to_numpy:
+            return BatchFeature({k: (v.numpy() if not v.is_cuda else v.cpu().numpy()) for k, v in data.items()})
+        return BatchFeature(data)
 
 
 class B200SeamlessM4TFeatureExtractor(_B200ExtractorBase):
@@ -237,23 +318,45 @@ class B200SeamlessM4TFeatureExtractor(_B200ExtractorBase):
 
     def __call__(self, raw_speech, padding=True, pad_to_multiple_of=2, max_length=None, truncation=False,
                  return_tensors=None, sampling_rate=None, return_attention_mask=None,
-                 do_normalize_per_mel_bins=True, **kwargs):
+                 do_normalize_per_mel_bins=True, output=None, **kwargs):
+        """``output="host"`` (implied by ``return_tensors="np"``) returns pinned CPU tensors through the chunked
+        H2D | kernels | D2H pipeline; the default for ``"pt"`` keeps the tensors on the CUDA device."""
         self._check_rate(sampling_rate)
-        self._device()                       # fail loudly before any host work when there is no GPU
+        dev = self._device()                 # fail loudly before any host work when there is no GPU
+        to_numpy, on_host = self._check_return(return_tensors, output)
         return_attention_mask = self.return_attention_mask if return_attention_mask is None else return_attention_mask
         if isinstance(raw_speech, PackedClips):
             packed = raw_speech
         else:
             packed = self.pack(_as_clip_list(raw_speech, 3, self.__class__.__name__))
-        pcm_d, off_d, len_d = self.to_device(packed)
         frames = np.array([ops.k_num_frames(int(n)) for n in packed.lengths], dtype=np.int64)
         T_pad, _ = self._padded_frames(frames, padding, max_length, truncation, pad_to_multiple_of)
+        B = packed.batch_size
+        if on_host and not packed.pcm.is_cuda and B > 0:
+            feats = torch.empty((B, T_pad // 2, 160), dtype=torch.float32, device=dev)
+            mask = torch.empty((B, T_pad // 2), dtype=torch.int32, device=dev) if return_attention_mask else None
+            h_feats = torch.empty((B, T_pad // 2, 160), dtype=torch.float32, pin_memory=True)
+            h_mask = torch.empty((B, T_pad // 2), dtype=torch.int32, pin_memory=True) if return_attention_mask else None
+
+            def launch(pcm_c, off_c, len_c, b0, b1, max_len):
+                ops.fbank_k(pcm_c, off_c, len_c, max_len, T_pad, self.padding_value, bool(do_normalize_per_mel_bins),
+                            want_mask=bool(return_attention_mask), out=feats[b0:b1],
+                            mask=mask[b0:b1] if mask is not None else None)
+
+            self._pipeline(packed, launch, [(feats, h_feats)] + ([(mask, h_mask)] if mask is not None else []))
+            data = {"input_features": h_feats}
+            if return_attention_mask:
+                data["attention_mask"] = h_mask
+            return self._finish(data, to_numpy)
+        pcm_d, off_d, len_d = self.to_device(packed)
         feats, mask = ops.fbank_k(pcm_d, off_d, len_d, packed.max_length, T_pad, self.padding_value,
                                   bool(do_normalize_per_mel_bins), want_mask=bool(return_attention_mask))
         data = {"input_features": feats}
         if return_attention_mask:
             data["attention_mask"] = mask
-        return self._finish(data, return_tensors)
+        if on_host:
+            data = {k: v.cpu() for k, v in data.items()}
+        return self._finish(data, to_numpy)
 
 
 class B200WhisperFeatureExtractor(_B200ExtractorBase):
@@ -283,9 +386,10 @@ class B200WhisperFeatureExtractor(_B200ExtractorBase):
 
     def __call__(self, raw_speech, truncation=True, pad_to_multiple_of=None, return_tensors=None,
                  return_attention_mask=None, padding="max_length", max_length=None, sampling_rate=None,
-                 do_normalize=None, device="cpu", **kwargs):
+                 do_normalize=None, device="cpu", output=None, **kwargs):
         self._check_rate(sampling_rate)
-        self._device()
+        dev = self._device()
+        to_numpy, on_host = self._check_return(return_tensors, output)
         if do_normalize:
             raise ValueError("do_normalize (waveform zero-mean/unit-variance) is not part of the hot path")
         if padding != "max_length" or not truncation:
@@ -299,10 +403,28 @@ class B200WhisperFeatureExtractor(_B200ExtractorBase):
             packed = raw_speech
         else:
             packed = self.pack(_as_clip_list(raw_speech, 2, self.__class__.__name__))
-        pcm_d, off_d, len_d = self.to_device(packed)
         want_mask = bool(return_attention_mask if return_attention_mask is not None else self.return_attention_mask)
+        B, T = packed.batch_size, n_samples // self.hop_length
+        if on_host and not packed.pcm.is_cuda and B > 0:
+            feats = torch.empty((B, 80, T), dtype=torch.float32, device=dev)
+            mask = torch.empty((B, T), dtype=torch.int32, device=dev) if want_mask else None
+            h_feats = torch.empty((B, 80, T), dtype=torch.float32, pin_memory=True)
+            h_mask = torch.empty((B, T), dtype=torch.int32, pin_memory=True) if want_mask else None
+
+            def launch(pcm_c, off_c, len_c, b0, b1, max_len):
+                ops.logmel_w(pcm_c, off_c, len_c, n_samples, want_mask=want_mask, out=feats[b0:b1],
+                             mask=mask[b0:b1] if mask is not None else None)
+
+            self._pipeline(packed, launch, [(feats, h_feats)] + ([(mask, h_mask)] if mask is not None else []))
+            data = {"input_features": h_feats}
+            if want_mask:
+                data["attention_mask"] = h_mask
+            return self._finish(data, to_numpy)
+        pcm_d, off_d, len_d = self.to_device(packed)
         feats, mask = ops.logmel_w(pcm_d, off_d, len_d, n_samples, want_mask=want_mask)
         data = {"input_features": feats}
         if want_mask:
             data["attention_mask"] = mask
-        return self._finish(data, return_tensors)
+        if on_host:
+            data = {k: v.cpu() for k, v in data.items()}
+        return self._finish(data, to_numpy)

@@ -101,7 +101,8 @@ def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max
 
 
 def logmel_w(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, n_samples: int = 480000,
-             want_mask: bool = False, peak: torch.Tensor | None = None, out: torch.Tensor | None = None):
+             want_mask: bool = False, peak: torch.Tensor | None = None, out: torch.Tensor | None = None,
+             mask: torch.Tensor | None = None):
     """Recipe W on device-resident packed PCM -> (float32 [B, 80, n_samples/160], int32 mask or None)."""
     lib = _lib.load()
     _require_cuda(pcm, "pcm", torch.float32)
@@ -114,7 +115,10 @@ def logmel_w(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, n_
         out = torch.empty((B, W_NMEL, T), dtype=torch.float32, device=dev)
     else:
         _require_cuda(out, "out", torch.float32)
-    mask = torch.empty((B, T), dtype=torch.int32, device=dev) if want_mask else None
+    if want_mask and mask is None:
+        mask = torch.empty((B, T), dtype=torch.int32, device=dev)
+    if mask is not None:
+        _require_cuda(mask, "mask", torch.int32)
     if peak is not None:
         _require_cuda(peak, "peak", torch.float32)
     nbytes = C.c_size_t(0)

@@ -152,3 +152,22 @@ def test_unaligned_clip_offsets_take_the_plain_load_path(fe, cuda_device):
                        int(lengths.max()), T_pad)
     ref = OK.extract(clips)
     _check({"input_features": x.cpu().numpy(), "attention_mask": m.cpu().numpy()}, *ref)
+
+
+def test_host_output_pipeline_is_bit_identical(fe):
+    """output='host' / return_tensors='np' go through the chunked H2D | kernels | D2H pipeline: same bits as the
+    single-shot device path, pinned CPU tensors, several chunks."""
+    clips = synth.batch_variable(9, seed=21, whole_seconds=False, max_s=4) + [synth.clip("G", 719, 3)]
+    dev_out = fe(clips, sampling_rate=16000, return_tensors="pt")
+    old = fe.CHUNK_BYTES
+    try:
+        for chunk_bytes in (1, 300000, old):
+            type(fe).CHUNK_BYTES = chunk_bytes
+            host = fe(clips, sampling_rate=16000, return_tensors="pt", output="host")
+            assert not host["input_features"].is_cuda and host["input_features"].is_pinned()
+            assert torch.equal(host["input_features"], dev_out["input_features"].cpu())
+            assert torch.equal(host["attention_mask"], dev_out["attention_mask"].cpu())
+            as_np = fe(clips, sampling_rate=16000, return_tensors="np")
+            assert np.array_equal(as_np["input_features"], dev_out["input_features"].cpu().numpy())
+    finally:
+        type(fe).CHUNK_BYTES = old

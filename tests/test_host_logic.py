@@ -80,3 +80,18 @@ def test_shard_clips_partitions_and_balances():
     assert load.max() / load.mean() < 1.01
     parts = [lens[s][:, None] for s in shards]
     assert np.array_equal(sharding.unshard(parts, shards)[:, 0], lens)
+
+
+def test_chunk_bounds_cover_every_clip_once():
+    lengths = np.array([480000] * 10 + [16000, 400, 32000], np.int32)
+    offsets, _ = _layout(lengths)
+    fe = B200SeamlessM4TFeatureExtractor
+    for chunk_bytes in (1, 4 * 480000, 12 << 20, 1 << 40):
+        bounds = fe.chunk_bounds(offsets, lengths, chunk_bytes)
+        assert bounds[0][0] == 0 and bounds[-1][1] == lengths.size
+        assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:])) and all(b1 > b0 for b0, b1 in bounds)
+        for b0, b1 in bounds:
+            if b1 - b0 > 1:
+                assert (offsets[b1 - 1] + lengths[b1 - 1] - offsets[b0]) * 4 <= chunk_bytes
+    assert len(fe.chunk_bounds(offsets, lengths, 1)) == lengths.size
+    assert len(fe.chunk_bounds(offsets, lengths, 1 << 40)) == 1

@@ -59,3 +59,19 @@ def test_full_size_properties(fe):
     assert torch.equal(alone[0], x[5])
     ref, _ = OW.extract([clips[5]])
     assert np.abs(x[5].cpu().numpy() - ref[0]).max() <= TOL
+
+
+def test_host_output_pipeline_is_bit_identical(cuda_device):
+    fe = B200WhisperFeatureExtractor(device=cuda_device)
+    clips = [synth.clip("G", 16000, 1), synth.clip("AM", 9000, 2), synth.clip("U", 20000, 3)]
+    dev_out = fe(clips, sampling_rate=16000, return_tensors="pt", max_length=16000, return_attention_mask=True)
+    old = fe.CHUNK_BYTES
+    try:
+        type(fe).CHUNK_BYTES = 1
+        host = fe(clips, sampling_rate=16000, return_tensors="pt", max_length=16000, return_attention_mask=True,
+                  output="host")
+        assert host["input_features"].is_pinned()
+        assert torch.equal(host["input_features"], dev_out["input_features"].cpu())
+        assert torch.equal(host["attention_mask"], dev_out["attention_mask"].cpu())
+    finally:
+        type(fe).CHUNK_BYTES = old
