@@ -5,11 +5,12 @@
 // R/cv_inference.py:105, R/training/trainer_unfreeze.py:1073-1074); the N x M matrix is the
 // north_star's superset whose diagonal equals the pairwise scores.
 //
-//   c_row_norms   one warp per row: 1 / max(||x||, 1e-12) and the "some norm is off by > 1e-4" flag
+//   c_row_norms   one warp per row (both operands in one launch): 1 / max(||x||, 1e-12) and the "some norm is off by > 1e-4" flag
 //                 (torch.allclose(norm, 1, atol=1e-4): |norm - 1| <= 1e-4 + 1e-5)
 //   c_pairwise    one warp per row: <a_i, b_i> * inv_a[i] * inv_b[i]
-//   c_nxm_f32     float32 tiled contraction (CUDA cores), epilogue scales by inv_a[i] * inv_b[j]
+//   c_split + c_nxm_tc   the N x M matrix on tcgen05 tensor cores with split-TF32 operands (see below)
 #include "stx_common.h"
+#include <cuda.h>
 
 namespace stx {
 namespace {
@@ -25,16 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void c_clear_flags(CosWs* ws) {
-    if (threadIdx.x == 0) { ws->flag_a = 0; ws->flag_b = 0; }
-}
-
-__global__ void __launch_bounds__(256)
-c_row_norms(const float* __restrict__ x, int rows, int D, float* __restrict__ inv, int* __restrict__ flag) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    const float* p = x + (size_t)row * D;
+__device__ __forceinline__ float row_sumsq(const float* __restrict__ p, int D, int lane) {
     float acc = 0.0f;
     if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
         const float4* p4 = reinterpret_cast<const float4*>(p);
@@ -45,11 +37,23 @@ c_row_norms(const float* __restrict__ x, int rows, int D, float* __restrict__ in
     } else {
         for (int i = lane; i < D; i += 32) { const float v = __ldg(p + i); acc = fmaf(v, v, acc); }
     }
-    acc = warp_sum(acc);
+    return warp_sum(acc);
+}
+
+// rows [0, N) are operand a, rows [N, N + M) operand b (one launch for both)
+__global__ void __launch_bounds__(256)
+c_row_norms(const float* __restrict__ a, const float* __restrict__ b, int N, int M, int D, float* __restrict__ inv_a,
+            float* __restrict__ inv_b, CosWs* __restrict__ ws) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= N + M) return;
+    const bool is_b = row >= N;
+    if (is_b) row -= N;
+    const float acc = row_sumsq((is_b ? b : a) + (size_t)row * D, D, lane);
     if (lane == 0) {
         const float nrm = sqrtf(acc);
-        inv[row] = 1.0f / fmaxf(nrm, 1e-12f);
-        if (!(fabsf(nrm - 1.0f) <= 1e-4f + 1e-5f)) atomicOr(flag, 1);
+        (is_b ? inv_b : inv_a)[row] = 1.0f / fmaxf(nrm, 1e-12f);
+        if (!(fabsf(nrm - 1.0f) <= 1e-4f + 1e-5f)) atomicOr(is_b ? &ws->flag_b : &ws->flag_a, 1);
     }
 }
 
@@ -80,54 +84,218 @@ c_pairwise(const float* __restrict__ a, const float* __restrict__ b, int N, int 
     }
 }
 
-// S[i, j] = <a_i, b_j> * inv_a[i] * inv_b[j];  64 x 64 tile per CTA, 4 x 4 per thread, K step 16
-constexpr int kBM = 64, kBN = 64, kBK = 16;
+// ---- N x M contraction on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) -------------------
+//
+// float32 accuracy from TF32 MMAs by operand splitting: x = hi + lo with hi = x truncated to TF32 (exactly
+// representable, so the tensor core's own fp32 -> tf32 conversion cannot change it) and lo = x - hi (exact);
+//   <a, b> ~= <a_hi, b_hi> + <a_lo, b_hi> + <a_hi, b_lo>          (the dropped <a_lo, b_lo> is ~2^-22 |a||b|)
+// run as ONE accumulation of 3 * D/32 k-blocks into the same TMEM tile.  Measured max-abs error vs float64 on
+// unit rows: ~2e-7 (single-pass TF32: 5e-5; the bar is 1e-5).
+//
+//   c_split    one warp per row: scale by 1/||x|| (or 1), write hi and lo planes with rows zero-padded to a
+//              multiple of 32 floats (one 128-byte swizzle row per k-block)
+//   c_nxm_tc   128 x 128 tile per CTA, 192 threads: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B,
+//              3-stage full/empty mbarrier ring), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer
+//              (kind::tf32, M = 128, N = 128, K = 8; tcgen05.commit frees the stage), warps 2-5 = epilogue
+//              (tcgen05.ld 32x32b.x32 -> registers -> 128-byte row segments of S)
+constexpr int kTM = 128, kTN = 128, kTK = 32, kStages = 3;
+constexpr int kTcThreads = 192;
+constexpr int kTileABytes = kTM * kTK * 4, kTileBBytes = kTN * kTK * 4;
+constexpr unsigned kTmemCols = 128;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major A and B,
+// N >> 3 at [17,23), M >> 4 at [24,29)
+constexpr unsigned kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTN >> 3) << 17) | ((unsigned)(kTM >> 4) << 24);
+
+struct TcSmem {
+    unsigned char a[kStages][kTileABytes];      // [128 rows][128 B], 128-byte swizzle, 1024-byte aligned
+    unsigned char b[kStages][kTileBBytes];
+    unsigned long long full[kStages], empty[kStages], tmem_full;
+    unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor) of a K-major tile with 128-byte swizzle: start address
+// >> 4 at [0,14), leading byte offset (unused for swizzled K-major) = 1 at [16,30), stride byte offset = 1024 B (8 rows)
+// >> 4 at [32,46), version 1 at [46,48), layout SWIZZLE_128B = 2 at [61,64)
+__device__ __forceinline__ unsigned long long umma_desc(const void* tile, int k_bytes) {
+    const unsigned addr = smem_u32(tile) + (unsigned)k_bytes;
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// hi / lo planes of both operands (rows [0, N) = a, [N, N + M) = b), rows zero-padded to Dp floats.  inv == nullptr:
+// normalise unconditionally with the norm computed here (no separate norm pass, no flags).
 __global__ void __launch_bounds__(256)
-c_nxm_f32(const float* __restrict__ a, const float* __restrict__ b, int N, int M, int D,
-          const float* __restrict__ inv_a, const float* __restrict__ inv_b, const CosWs* __restrict__ ws, int always,
-          float* __restrict__ S) {
-    __shared__ float As[kBK][kBM + 4];
-    __shared__ float Bs[kBK][kBN + 4];
-    const int tid = threadIdx.x;
-    const int i0 = blockIdx.y * kBM, j0 = blockIdx.x * kBN;
-    const int ty = tid >> 4, tx = tid & 15;
-    float acc[4][4] = {};
-    // loader: 64 rows x 16 k = 1024 elements per operand, 4 per thread
-    const int lrow = tid >> 2, lk = (tid & 3) * 4;
-    for (int k0 = 0; k0 < D; k0 += kBK) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = k0 + lk + e;
-            const int ia = i0 + lrow, jb = j0 + lrow;
-            As[lk + e][lrow] = (ia < N && k < D) ? __ldg(a + (size_t)ia * D + k) : 0.0f;
-            Bs[lk + e][lrow] = (jb < M && k < D) ? __ldg(b + (size_t)jb * D + k) : 0.0f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kBK; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int y = 0; y < 4; ++y)
-#pragma unroll
-                for (int x = 0; x < 4; ++x) acc[y][x] = fmaf(ar[y], br[x], acc[y][x]);
-        }
-        __syncthreads();
-    }
-    const bool na = always || ws->flag_a, nb = always || ws->flag_b;
-#pragma unroll
-    for (int y = 0; y < 4; ++y) {
-        const int i = i0 + ty * 4 + y;
-        if (i >= N) continue;
-        const float sa = na ? inv_a[i] : 1.0f;
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-            const int j = j0 + tx * 4 + x;
-            if (j < M) S[(size_t)i * M + j] = acc[y][x] * sa * (nb ? inv_b[j] : 1.0f);
-        }
+c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, int D, int Dp,
+        const float* __restrict__ inv_a, const float* __restrict__ inv_b, const CosWs* __restrict__ ws,
+        float* __restrict__ a_hi, float* __restrict__ a_lo, float* __restrict__ b_hi, float* __restrict__ b_lo) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= N + M) return;
+    const bool is_b = row >= N;
+    if (is_b) row -= N;
+    const float* p = (is_b ? b : a) + (size_t)row * D;
+    float scale;
+    if (inv_a == nullptr) scale = 1.0f / fmaxf(sqrtf(row_sumsq(p, D, lane)), 1e-12f);
+    else scale = (is_b ? ws->flag_b : ws->flag_a) ? (is_b ? inv_b : inv_a)[row] : 1.0f;
+    float* ph = (is_b ? b_hi : a_hi) + (size_t)row * Dp;
+    float* pl = (is_b ? b_lo : a_lo) + (size_t)row * Dp;
+    for (int i = lane; i < Dp; i += 32) {
+        const float v = i < D ? __ldg(p + i) * scale : 0.0f;
+        const float h = __int_as_float(__float_as_int(v) & 0xffffe000);     // TF32: 10 explicit mantissa bits
+        ph[i] = h;
+        pl[i] = v - h;
     }
 }
+
+__global__ void __launch_bounds__(kTcThreads)
+c_nxm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+         int N, int M, int kb_per_pass, float* __restrict__ S) {
+    extern __shared__ unsigned char smem_raw[];
+    TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+    const int num_kb = 3 * kb_per_pass;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+            mbar_init(&sm.tmem_full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages, it = kb / kStages;
+                if (it > 0) mbar_wait(&sm.empty[s], (unsigned)(it - 1) & 1u);
+                const int pass = kb / kb_per_pass, k0 = (kb - pass * kb_per_pass) * kTK;
+                mbar_expect_tx(&sm.full[s], kTileABytes + kTileBBytes);
+                tma_load_2d(sm.a[s], pass == 1 ? &map_a_lo : &map_a_hi, k0, m0, &sm.full[s]);
+                tma_load_2d(sm.b[s], pass == 2 ? &map_b_lo : &map_b_hi, k0, n0, &sm.full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages, it = kb / kStages;
+                mbar_wait(&sm.full[s], (unsigned)it & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < kTK / 8; ++k)
+                    umma_tf32(tmem, umma_desc(sm.a[s], k * 32), umma_desc(sm.b[s], k * 32), (kb | k) != 0);
+                umma_commit(&sm.empty[s]);          // the stage is free once these MMAs have read it
+            }
+            umma_commit(&sm.tmem_full);             // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(&sm.tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                     // a warp can only read its own quarter of the TMEM lanes
+        const int row = m0 + q * 32 + lane;
+        const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTN; c0 += 32) {
+            unsigned r[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                         : "r"(tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < N) {
+                float* dst = S + (size_t)row * M + n0 + c0;
+                if (vec && n0 + c0 + 32 <= M) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j < M) dst[j] = __uint_as_float(r[j]);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_map(CUtensorMap* map, const float* base, int rows, int Dp, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        STX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available"); return STX_EDEVICE; }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Dp * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STX_EINVAL; }
+    return 0;
+}
+
+inline int padded_d(int D) { return (D + kTK - 1) / kTK * kTK; }
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -139,12 +307,14 @@ extern "C" {
 int stx_cosine_workspace(int N, int M, int D, size_t* bytes) {
     using namespace stx;
     if (N < 0 || M < 0 || D < 0 || !bytes) { set_error("stx_cosine_workspace: bad argument"); return STX_EINVAL; }
-    *bytes = align256(sizeof(CosWs)) + align256(size_t(N) * sizeof(float)) + align256(size_t(M) * sizeof(float));
+    const size_t Dp = size_t(padded_d(D));
+    *bytes = align256(sizeof(CosWs)) + align256(size_t(N) * sizeof(float)) + align256(size_t(M) * sizeof(float)) +
+             2 * align256(size_t(N) * Dp * sizeof(float)) + 2 * align256(size_t(M) * Dp * sizeof(float));
     return 0;
 }
 
 static int cosine_prepare(const float* d_a, const float* d_b, int N, int M, int D, void* d_ws, size_t ws_bytes,
-                          cudaStream_t st, stx::CosWs** ws, float** inv_a, float** inv_b) {
+                          cudaStream_t st, stx::CosWs** ws, float** inv_a, float** inv_b, bool with_norms = true) {
     using namespace stx;
     size_t need = 0;
     stx_cosine_workspace(N, M, D, &need);
@@ -153,9 +323,10 @@ static int cosine_prepare(const float* d_a, const float* d_b, int N, int M, int 
     *ws = reinterpret_cast<CosWs*>(base);
     *inv_a = reinterpret_cast<float*>(base + align256(sizeof(CosWs)));
     *inv_b = reinterpret_cast<float*>(base + align256(sizeof(CosWs)) + align256(size_t(N) * sizeof(float)));
-    STX_LAUNCH(c_clear_flags, dim3(1), dim3(32), 0, st, *ws);
-    STX_LAUNCH(c_row_norms, dim3((N + 7) / 8), dim3(256), 0, st, d_a, N, D, *inv_a, &(*ws)->flag_a);
-    STX_LAUNCH(c_row_norms, dim3((M + 7) / 8), dim3(256), 0, st, d_b, M, D, *inv_b, &(*ws)->flag_b);
+    if (with_norms) {
+        STX_CUDA(cudaMemsetAsync(*ws, 0, sizeof(CosWs), st));
+        STX_LAUNCH(c_row_norms, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, *inv_a, *inv_b, *ws);
+    }
     return 0;
 }
 
@@ -182,9 +353,30 @@ int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int 
     if (int rc = check_device()) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CosWs* ws; float *inv_a, *inv_b;
-    if (int rc = cosine_prepare(d_a, d_b, N, M, D, d_ws, ws_bytes, st, &ws, &inv_a, &inv_b)) return rc;
-    STX_LAUNCH(c_nxm_f32, dim3((M + kBN - 1) / kBN, (N + kBM - 1) / kBM), dim3(256), 0, st,
-               d_a, d_b, N, M, D, inv_a, inv_b, ws, always_normalize, d_S);
+    if (int rc = cosine_prepare(d_a, d_b, N, M, D, d_ws, ws_bytes, st, &ws, &inv_a, &inv_b, !always_normalize)) return rc;
+    const int Dp = padded_d(D);
+    char* p = reinterpret_cast<char*>(inv_b) + align256(size_t(M) * sizeof(float));
+    float* a_hi = reinterpret_cast<float*>(p);  p += align256(size_t(N) * Dp * sizeof(float));
+    float* a_lo = reinterpret_cast<float*>(p);  p += align256(size_t(N) * Dp * sizeof(float));
+    float* b_hi = reinterpret_cast<float*>(p);  p += align256(size_t(M) * Dp * sizeof(float));
+    float* b_lo = reinterpret_cast<float*>(p);
+    STX_LAUNCH(c_split, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
+               always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, a_hi, a_lo, b_hi, b_lo);
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    if (int rc = make_map(&ma_hi, a_hi, N, Dp, kTM)) return rc;
+    if (int rc = make_map(&ma_lo, a_lo, N, Dp, kTM)) return rc;
+    if (int rc = make_map(&mb_hi, b_hi, M, Dp, kTN)) return rc;
+    if (int rc = make_map(&mb_lo, b_lo, M, Dp, kTN)) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    STX_CUDA(cudaGetDevice(&dev));
+    const int smem_bytes = (int)sizeof(TcSmem) + 1024;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STX_CUDA(cudaFuncSetAttribute(c_nxm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set[dev] = true;
+    }
+    STX_LAUNCH(c_nxm_tc, dim3((M + kTN - 1) / kTN, (N + kTM - 1) / kTM), dim3(kTcThreads), smem_bytes, st,
+               ma_hi, ma_lo, mb_hi, mb_lo, N, M, Dp / kTK, d_S);
     return 0;
 }
 

@@ -53,7 +53,8 @@ def test_diagonal_equals_pairwise(cuda_device):
     ad, bd = _dev(a, cuda_device), _dev(b, cuda_device)
     S = scoring.cosine_matrix(ad, bd)
     p = ops.cosine_pairwise(ad, bd, always_normalize=True)
-    assert (S.diagonal() - p).abs().max().item() <= 2e-6
+    # tensor-core (split-TF32, fp32 accumulate in TMEM) matrix vs CUDA-core pairwise: both within 1e-5 of float64
+    assert (S.diagonal() - p).abs().max().item() <= 5e-6
     assert np.abs(p.cpu().numpy() - OC.pairwise_reference(a, b)).max() <= TOL
 
 
