@@ -96,6 +96,17 @@ int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_l
                 int max_length, const float* d_peak, int T_pad, float padding_value, int normalize,
                 float* d_out, int32_t* d_mask, void* d_ws, size_t ws_bytes, void* stream);
 
+/* The trainer's audio collate fused into the same kernels.  Replaces the per-item extractor call of
+ * CommonVoiceDataset.__getitem__ (R/training/trainer_unfreeze.py:855-866: one clip per call, no peak-normalise, no
+ * trim) followed by custom_collate_fn's audio padding (R/training/trainer_unfreeze.py:898-908):
+ *   d_out   [B, T_pad/2, 160] float32: the clip's stacked frames as the single-clip call returns them (the second half
+ *           of the last stacked frame of an odd-T clip is padding_value), ZERO rows after them
+ *   d_mask  [B, T_pad/2] int64: 1 for every stacked frame of the clip (ceil(T_b / 2) of them), else 0
+ * T_pad = 2 * max_b ceil(T_b / 2).  Workspace as for stx_fbank_k. */
+int stx_fbank_k_collate(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B,
+                        int max_length, int T_pad, float padding_value, float* d_out, int64_t* d_mask,
+                        void* d_ws, size_t ws_bytes, void* stream);
+
 /* Per-clip max(1, max|x|) -> d_peak[b] (float32): the divisor of R/processor.py:91-92
  * (division only happens when max|x| > 1; dividing by exactly 1.0f is the identity). */
 int stx_peak_abs(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B,

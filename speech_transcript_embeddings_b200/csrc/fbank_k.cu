@@ -14,9 +14,10 @@
 // Three kernels:
 //   k_frames    one CTA per (clip, chunk of frames): PCM -> raw log-mel (written in place into the
 //               output tensor, whose [T_pad/2,160] rows are exactly [T_pad,80] rows) + per-chunk
-//               per-bin (sum, sum of squares) partials in float64
-//   k_finalize  one CTA per clip: ordered reduction of the partials -> mean, 1/sqrt(var_ddof1 + 1e-7)
-//   k_normalize in-place CMVN, padding rows, attention mask
+//               per-bin (sum, sum of squares) partials in fixed point (int64)
+//   k_finalize  one CTA per clip: integer sum of the partials -> mean, 1/sqrt(var_ddof1 + 1e-7)
+//   k_normalize in-place CMVN, padding rows, attention mask (the extractor's int32 mask, or the trainer
+//               collate's int64 mask with zero rows past the clip: R/training/trainer_unfreeze.py:898-908)
 //
 // k_frames keeps ONE FRAME PER LANE: a tile is 32 consecutive frames of a clip and the 16 warps of the
 // CTA split each frame's 512-point real FFT (n = 16 n1 + n2, k = k1 + 32 k2) between them, so every
@@ -128,6 +129,19 @@ __device__ __forceinline__ float ln_pos(float x) {
 
 // ---- mbarrier + 1-D bulk copy (TMA) ---------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// Shared-memory loads that keep their program order (volatile asm): all 16 warps of the CTA issue their exchange loads
+// at the same time, so the LSU returns a warp's j-th load after ~16 j wavefronts; issuing them in the order the
+// butterflies first use them lets the FP64 work start before the last load has landed.
+__device__ __forceinline__ double lds_f64(const double* p) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(const double2* p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -272,11 +286,18 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             const double* D = sm.u.d + kDRow * lane + warp;
             double y[25];
             double sa = 0.0, sb = 0.0;
+            // first-use order of the radix-4 decimation in time: y[q], y[q+16], y[q+8], y[q+24], y[q+4], y[q+20], y[q+12]
+            constexpr int kOrder1[25] = {0, 16, 8, 24, 4, 20, 12, 1, 17, 9, 5, 21, 13, 2, 18, 10, 6, 22, 14, 3, 19, 11, 7, 23, 15};
+            double v1[25];
+#pragma unroll
+            for (int j = 0; j < 25; ++j) {
+                const int n1 = kOrder1[j];
+                v1[n1] = lds_f64(D + 16 * n1 + (n1 >= 10) + (n1 >= 20));
+            }
 #pragma unroll
             for (int n1 = 0; n1 < 25; ++n1) {
-                const double v = D[16 * n1 + (n1 >= 10) + (n1 >= 20)];
-                y[n1] = c_win[warp][n1] * v;
-                if (n1 & 1) sb += v; else sa += v;
+                y[n1] = c_win[warp][n1] * v1[n1];
+                if (n1 & 1) sb += v1[n1]; else sa += v1[n1];
             }
             sm.psum[lane][warp] = sa + sb;
             double re[17], im[17];
@@ -328,9 +349,11 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 for (int k2 = 0; k2 < 8; ++k2) put(16 + 32 * k2, e16r[k2], e16i[k2], c_wh[0][8 + k2]);
             } else {
                 double xr[16], xi[16], yr[16], yi[16];
+                constexpr int kOrder2[16] = {0, 8, 4, 12, 1, 9, 5, 13, 2, 10, 6, 14, 3, 11, 7, 15};
 #pragma unroll
-                for (int n2 = 0; n2 < 16; ++n2) {
-                    const double2 v = sm.ex[warp - 1][n2][lane];
+                for (int j = 0; j < 16; ++j) {
+                    const int n2 = kOrder2[j];
+                    const double2 v = lds_v2f64(&sm.ex[warp - 1][n2][lane]);
                     xr[n2] = v.x; xi[n2] = v.y;
                 }
                 codelets::dft16<double>(xr, xi, yr, yi);
@@ -424,13 +447,20 @@ __global__ void k_finalize(const int* __restrict__ lengths, const long long* __r
 }
 
 // in-place CMVN + padding rows + mask.  One thread per float4 of a clip's [T_pad, 80] block.
+//   rows t < T            normalised features
+//   rows T <= t < T2      padding_value (T2 = T rounded up to even: the half of the last stacked frame of an odd clip)
+//   rows t >= T2          tail_value (= padding_value for the extractor, …seamless_m4t.py:267-275; 0 for the trainer's
+//                         collate, R/training/trainer_unfreeze.py:902)
+//   mask_mode 0: int32, mask[j] = (2 j + 1 < T)  (…seamless_m4t.py:292-293);  1: int64, mask[j] = (2 j < T), i.e. every
+//   stacked frame the per-clip extractor call returned (R/training/trainer_unfreeze.py:904-908)
 __global__ void __launch_bounds__(256)
 k_normalize(const int* __restrict__ lengths, const double* __restrict__ stats, int T_pad, float padding_value,
-            int normalize, float* __restrict__ out, int* __restrict__ mask) {
+            float tail_value, int normalize, float* __restrict__ out, void* __restrict__ mask, int mask_mode) {
     __shared__ double s_mean[kMel], s_rstd[kMel];
     const int b = blockIdx.y;
     const int n = lengths[b];
     const int T = min(n >= kFrame ? 1 + (n - kFrame) / kHop : 0, T_pad);
+    const int T2 = min((T + 1) & ~1, T_pad);
     if (threadIdx.x < kMel) {
         s_mean[threadIdx.x] = stats[((size_t)b * kMel + threadIdx.x) * 2 + 0];
         s_rstd[threadIdx.x] = stats[((size_t)b * kMel + threadIdx.x) * 2 + 1];
@@ -449,14 +479,17 @@ k_normalize(const int* __restrict__ lengths, const double* __restrict__ stats, i
             v.z = (float)(((double)v.z - s_mean[m + 2]) * s_rstd[m + 2]);
             v.w = (float)(((double)v.w - s_mean[m + 3]) * s_rstd[m + 3]);
         } else {
-            v = make_float4(padding_value, padding_value, padding_value, padding_value);
+            const float f = t < T2 ? padding_value : tail_value;
+            v = make_float4(f, f, f, f);
         }
         o4[q] = v;
     }
     if (mask) {
         const int rows = T_pad / 2;
-        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < rows; j += gridDim.x * blockDim.x)
-            mask[(size_t)b * rows + j] = (2 * j + 1 < T) ? 1 : 0;
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < rows; j += gridDim.x * blockDim.x) {
+            if (mask_mode == 0) static_cast<int*>(mask)[(size_t)b * rows + j] = (2 * j + 1 < T) ? 1 : 0;
+            else static_cast<long long*>(mask)[(size_t)b * rows + j] = (2 * j < T) ? 1 : 0;
+        }
     }
 }
 
@@ -573,9 +606,9 @@ int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     return 0;
 }
 
-int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
-                const float* d_peak, int T_pad, float padding_value, int normalize, float* d_out,
-                int32_t* d_mask, void* d_ws, size_t ws_bytes, void* stream) {
+static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
+                        const float* d_peak, int T_pad, float padding_value, float tail_value, int normalize,
+                        float* d_out, void* d_mask, int mask_mode, void* d_ws, size_t ws_bytes, void* stream) {
     using namespace stx;
     if (B < 0 || max_length < 0 || T_pad < 0 || (T_pad & 1)) { set_error("stx_fbank_k: B, max_length >= 0 and even T_pad required"); return STX_EINVAL; }
     if (B == 0 || T_pad == 0) return 0;
@@ -616,9 +649,23 @@ int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_l
     STX_LAUNCH(k_finalize, dim3(B), dim3(96), 0, st, d_lengths, partials, chunk_frames, chunks, stats);
     const int quads = T_pad * (kMel / 4);
     const int gx = std::max(1, std::min((quads + 255) / 256, 64));
-    STX_LAUNCH(k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, stats, T_pad, padding_value, normalize,
-               d_out, d_mask);
+    STX_LAUNCH(k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, stats, T_pad, padding_value, tail_value, normalize,
+               d_out, d_mask, mask_mode);
     return 0;
+}
+
+int stx_fbank_k(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
+                const float* d_peak, int T_pad, float padding_value, int normalize, float* d_out,
+                int32_t* d_mask, void* d_ws, size_t ws_bytes, void* stream) {
+    return fbank_k_impl(d_pcm, d_offsets, d_lengths, B, max_length, d_peak, T_pad, padding_value, padding_value, normalize,
+                        d_out, d_mask, 0, d_ws, ws_bytes, stream);
+}
+
+int stx_fbank_k_collate(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
+                        int T_pad, float padding_value, float* d_out, int64_t* d_mask, void* d_ws, size_t ws_bytes,
+                        void* stream) {
+    return fbank_k_impl(d_pcm, d_offsets, d_lengths, B, max_length, nullptr, T_pad, padding_value, 0.0f, 1,
+                        d_out, d_mask, 1, d_ws, ws_bytes, stream);
 }
 
 int stx_peak_abs(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, float* d_peak,

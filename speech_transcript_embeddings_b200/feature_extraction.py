@@ -20,7 +20,10 @@ the call costs about max(H2D, D2H) over PCIe instead of their sum.
 from __future__ import annotations
 
 import logging
+import os
+import threading
 from collections import UserDict
+from concurrent.futures import ThreadPoolExecutor
 from typing import Sequence
 
 import numpy as np
@@ -49,13 +52,39 @@ class BatchFeature(UserDict):
         return self
 
 
-class PackedClips:
-    """Clips packed back to back (128-byte aligned) in one float32 buffer, plus per-clip offsets/lengths."""
+_pool = None
+_pool_lock = threading.Lock()
 
-    def __init__(self, pcm: torch.Tensor, offsets: np.ndarray, lengths: np.ndarray):
+
+def _copy_pool() -> ThreadPoolExecutor:
+    """Worker threads for host-side packing (NumPy's memcpy releases the GIL)."""
+    global _pool
+    with _pool_lock:
+        if _pool is None:
+            _pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)),
+                                       thread_name_prefix="stx-pack")
+        return _pool
+
+
+class PackedClips:
+    """Clips packed back to back (128-byte aligned) in one float32 buffer, plus per-clip offsets/lengths.
+
+    ``bounds`` / ``ready`` (optional): clip ranges whose packing is still running on worker threads, one future per
+    clip, grouped per range; consumers wait for a range right before they copy it to the device."""
+
+    def __init__(self, pcm: torch.Tensor, offsets: np.ndarray, lengths: np.ndarray, bounds=None, ready=None):
         self.pcm = pcm                      # pinned host tensor or CUDA tensor, float32 [total]
         self.offsets = offsets              # int64 [B] (host)
         self.lengths = lengths              # int32 [B] (host)
+        self.bounds = bounds
+        self.ready = ready
+
+    def wait(self, i: int | None = None):
+        if self.ready is None:
+            return
+        for group in (self.ready if i is None else [self.ready[i]]):
+            for f in group:
+                f.result()
 
     @property
     def batch_size(self) -> int:
@@ -178,7 +207,7 @@ class _B200ExtractorBase:
         cur = torch.cuda.current_stream(dev)
         for s_ in (s_in, s_run, s_out):
             s_.wait_stream(cur)                                  # buffers allocated on the caller's stream are ready
-        bounds = self.chunk_bounds(packed.offsets, packed.lengths)
+        bounds = packed.bounds if packed.bounds is not None else self.chunk_bounds(packed.offsets, packed.lengths)
         # chunk-relative offsets: every chunk is an independent call into the library
         rel = packed.offsets.copy()
         for b0, b1 in bounds:
@@ -194,9 +223,10 @@ class _B200ExtractorBase:
         with torch.cuda.stream(s_in):
             meta_d.copy_(meta, non_blocking=True)
         off_d, len_d = meta_d[:B], meta_d[B:2 * B].view(torch.int32)[:B]
-        for b0, b1 in bounds:
+        for ci, (b0, b1) in enumerate(bounds):
             lo = int(packed.offsets[b0])
             hi = int(packed.offsets[b1 - 1]) + int(packed.lengths[b1 - 1])
+            packed.wait(ci)                                      # this chunk's clips are in the pinned buffer
             with torch.cuda.stream(s_in):
                 pcm_d[lo:hi].copy_(packed.pcm[lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
@@ -214,20 +244,35 @@ class _B200ExtractorBase:
         cur.wait_stream(s_run)                                   # device buffers may be reused by the caller's stream
 
     # -- host -> device ----------------------------------------------------------------------
+    PACK_THREADS_MIN_BYTES = 4 << 20     # below this a plain loop is faster than handing work to the pool
+
     def pack(self, clips: Sequence[np.ndarray]) -> PackedClips:
-        """Copy clips into one pinned host buffer (reused across calls)."""
+        """Copy clips into one pinned host buffer (reused across calls).  Large batches are copied by worker
+        threads, one task per clip, and the returned object carries the futures grouped per pipeline chunk: the chunked pipeline
+        starts the H2D copy of chunk 0 while later chunks are still being packed."""
         lengths = np.fromiter((c.size for c in clips), dtype=np.int32, count=len(clips))
         offsets, total = _layout(lengths)
         pcm, _ = self._stage.get(total, 2 * len(clips))
         view = pcm.numpy()
-        for c, o in zip(clips, offsets):
-            view[o:o + c.size] = c
-        return PackedClips(pcm[:total], offsets, lengths)
+
+        def copy_range(b0, b1):
+            for i in range(b0, b1):
+                o = int(offsets[i])
+                view[o:o + clips[i].size] = clips[i]
+
+        if total * 4 < self.PACK_THREADS_MIN_BYTES or len(clips) < 2:
+            copy_range(0, len(clips))
+            return PackedClips(pcm[:total], offsets, lengths)
+        bounds = self.chunk_bounds(offsets, lengths)
+        pool = _copy_pool()
+        ready = [[pool.submit(copy_range, i, i + 1) for i in range(b0, b1)] for b0, b1 in bounds]   # in clip order
+        return PackedClips(pcm[:total], offsets, lengths, bounds, ready)
 
     def to_device(self, packed: PackedClips):
         """(pcm, offsets, lengths) on the device; one async copy for the PCM, one for the metadata."""
         dev = self._device()
         B = packed.batch_size
+        packed.wait()
         if packed.pcm.is_cuda:
             pcm_d = packed.pcm
         else:
@@ -357,6 +402,43 @@ class B200SeamlessM4TFeatureExtractor(_B200ExtractorBase):
         if on_host:
             data = {k: v.cpu() for k, v in data.items()}
         return self._finish(data, to_numpy)
+
+
+    def collate(self, speech_arrays, output=None):
+        """The audio half of the trainer's batch in one call.
+
+        Replaces one ``feature_extractor(speech_array, sampling_rate, return_tensors="pt")`` call per item in
+        ``CommonVoiceDataset.__getitem__`` (R/training/trainer_unfreeze.py:855-866; no peak-normalise, no trim)
+        plus the audio padding of ``custom_collate_fn`` (R/training/trainer_unfreeze.py:898-908): returns
+        ``{"input_values": float32 [B, max T', 160] zero-padded, "attention_mask_audio": int64 [B, max T']}``,
+        every stacked frame a per-clip call returns marked valid (the collate discards the extractor's own mask).
+        ``output="host"`` gives pinned CPU tensors through the chunked pipeline (what a DataLoader would hand to
+        ``.to(device, non_blocking=True)``, R/training/trainer_unfreeze.py:1059-1061); the default keeps them on the GPU.
+        """
+        dev = self._device()
+        if output not in (None, "device", "host"):
+            raise ValueError("output must be 'device' or 'host'")
+        packed = speech_arrays if isinstance(speech_arrays, PackedClips) else self.pack(
+            _as_clip_list(list(speech_arrays), 3, self.__class__.__name__))
+        B = packed.batch_size
+        frames = np.array([ops.k_num_frames(int(n)) for n in packed.lengths], dtype=np.int64)
+        T_pad = 2 * int(((frames + 1) // 2).max()) if B else 0
+        if output == "host" and not packed.pcm.is_cuda and B > 0:
+            feats = torch.empty((B, T_pad // 2, 160), dtype=torch.float32, device=dev)
+            mask = torch.empty((B, T_pad // 2), dtype=torch.int64, device=dev)
+            h_feats = torch.empty((B, T_pad // 2, 160), dtype=torch.float32, pin_memory=True)
+            h_mask = torch.empty((B, T_pad // 2), dtype=torch.int64, pin_memory=True)
+
+            def launch(pcm_c, off_c, len_c, b0, b1, max_len):
+                ops.fbank_k_collate(pcm_c, off_c, len_c, max_len, T_pad, self.padding_value, out=feats[b0:b1], mask=mask[b0:b1])
+
+            self._pipeline(packed, launch, [(feats, h_feats), (mask, h_mask)])
+            return {"input_values": h_feats, "attention_mask_audio": h_mask}
+        pcm_d, off_d, len_d = self.to_device(packed)
+        feats, mask = ops.fbank_k_collate(pcm_d, off_d, len_d, packed.max_length, T_pad, self.padding_value)
+        if output == "host":
+            feats, mask = feats.cpu(), mask.cpu()
+        return {"input_values": feats, "attention_mask_audio": mask}
 
 
 class B200WhisperFeatureExtractor(_B200ExtractorBase):

@@ -100,6 +100,36 @@ def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max
     return out, mask
 
 
+def fbank_k_collate(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_length: int, T_pad: int,
+                    padding_value: float = 0.0, out: torch.Tensor | None = None, mask: torch.Tensor | None = None):
+    """Recipe K with the trainer's collate fused in (R/training/trainer_unfreeze.py:855-866, 898-908):
+    (input_values float32 [B, T_pad/2, 160] zero-padded, attention_mask_audio int64 [B, T_pad/2])."""
+    lib = _lib.load()
+    _require_cuda(pcm, "pcm", torch.float32)
+    _require_cuda(offsets, "offsets", torch.int64)
+    _require_cuda(lengths, "lengths", torch.int32)
+    if T_pad < 0 or T_pad % 2:
+        raise ValueError("T_pad must be even and >= 0")
+    B = lengths.numel()
+    dev = pcm.device
+    if out is None:
+        out = torch.empty((B, T_pad // 2, 2 * K_NMEL), dtype=torch.float32, device=dev)
+    else:
+        _require_cuda(out, "out", torch.float32)
+    if mask is None:
+        mask = torch.empty((B, T_pad // 2), dtype=torch.int64, device=dev)
+    else:
+        _require_cuda(mask, "mask", torch.int64)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_fbank_k_workspace(B, int(max_length), C.byref(nbytes)), "stx_fbank_k_workspace")
+    ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_fbank_k_collate(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, int(max_length),
+                                           int(T_pad), float(padding_value), out.data_ptr(), mask.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "stx_fbank_k_collate")
+    return out, mask
+
+
 def logmel_w(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, n_samples: int = 480000,
              want_mask: bool = False, peak: torch.Tensor | None = None, out: torch.Tensor | None = None,
              mask: torch.Tensor | None = None):

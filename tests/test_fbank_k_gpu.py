@@ -171,3 +171,38 @@ def test_host_output_pipeline_is_bit_identical(fe):
             assert np.array_equal(as_np["input_features"], dev_out["input_features"].cpu().numpy())
     finally:
         type(fe).CHUNK_BYTES = old
+
+
+def _reference_trainer_batch(clips, padding_value):
+    """R/training/trainer_unfreeze.py:855-866 (one extractor call per item) + :898-908 (custom_collate_fn), oracle extractor."""
+    items = []
+    for c in clips:
+        with np.errstate(all="ignore"):
+            x, _ = OK.extract([c], padding_value=padding_value)
+        items.append(x[0])                                   # .squeeze(0): [T', 160]
+    max_t = max(a.shape[0] for a in items)
+    padded = np.zeros((len(items), max_t, 160), np.float32)
+    mask = np.zeros((len(items), max_t), np.int64)
+    for i, a in enumerate(items):
+        padded[i, :a.shape[0]] = a
+        mask[i, :a.shape[0]] = 1
+    return padded, mask
+
+
+@pytest.mark.parametrize("padding_value", [0.0, 1.0])
+def test_trainer_collate_fused(cuda_device, padding_value):
+    fe = B200SeamlessM4TFeatureExtractor(padding_value=padding_value, device=cuda_device)
+    clips = synth.batch_variable(7, seed=9, whole_seconds=False, max_s=3)
+    clips += [synth.clip("G", n, 40 + n) for n in (560, 719, 720, 880, 16160)]        # T = 2, 2, 3, 4, 99: odd and even
+    ref_x, ref_m = _reference_trainer_batch(clips, padding_value)
+    got = fe.collate(clips)
+    assert got["input_values"].is_cuda and got["attention_mask_audio"].dtype == torch.int64
+    x, m = got["input_values"].cpu().numpy(), got["attention_mask_audio"].cpu().numpy()
+    assert x.shape == ref_x.shape and np.array_equal(m, ref_m)
+    assert np.abs(x - ref_x).max() <= TOL
+    for i, c in enumerate(clips):                                               # zero rows past each clip, exactly
+        t = (ops.k_num_frames(c.size) + 1) // 2
+        assert not x[i, t:].any() and m[i, :t].all() and not m[i, t:].any()
+    host = fe.collate(clips, output="host")
+    assert host["input_values"].is_pinned() and torch.equal(host["input_values"], got["input_values"].cpu())
+    assert torch.equal(host["attention_mask_audio"], got["attention_mask_audio"].cpu())
