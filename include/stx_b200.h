@@ -145,6 +145,26 @@ int stx_cosine_pairwise(const float* d_a, const float* d_b, int N, int D, int al
 int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int always_normalize,
                    float* d_S, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU N x M scoring: this rank's stripe S[rows of a, all M] where the text embeddings b are sharded over
+ * `world` ranks of one NVLink/NVSwitch box (BASELINE.json configs[4]).  The reference has no collective; this is the
+ * north_star's "all-gathered N x M cosine matrix".  The all-gather is FUSED into the kernels over peer memory:
+ *   - every rank owns a symmetric buffer of stx_cosine_gather_sizes().symm_bytes bytes, mapped into all peers
+ *     (h_peer_symm[r] = rank r's buffer as addressable from THIS process; torch symmetric memory provides them);
+ *   - the normalise + TF32-split kernel writes this rank's text planes into its slot of EVERY peer's buffer with
+ *     P2P stores over NVLink and then releases flag[rank] = epoch on every peer;
+ *   - the tcgen05 GEMM visits its own columns first and, per source rank, acquires that rank's flag before the
+ *     first TMA load of its columns, so the math on arrived shards overlaps the transfers still in flight.
+ * `epoch` must increase by 1 per call on all ranks (start at 1; the buffer must be zeroed once after allocation),
+ * and the caller must keep a cross-rank barrier between the end of one call and the start of the next (a rank
+ * must not overwrite a slot that a peer is still reading).  h_counts[r] = rows of rank r's shard (<= m_cap).
+ * d_S is [n_local, sum(h_counts)] float32.  Rows are always L2-normalised.
+ * ------------------------------------------------------------------------------------------- */
+int stx_cosine_gather_sizes(int n_local, int m_cap, int world, int D, size_t* ws_bytes, size_t* symm_bytes);
+int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int D, int world, int rank,
+                            const int32_t* h_counts, int m_cap, void* const* h_peer_symm, uint32_t epoch,
+                            float* d_S, void* d_ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

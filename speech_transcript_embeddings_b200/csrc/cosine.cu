@@ -150,40 +150,102 @@ __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// hi / lo planes of both operands (rows [0, N) = a, [N, N + M) = b), rows zero-padded to Dp floats.  inv == nullptr:
-// normalise unconditionally with the norm computed here (no separate norm pass, no flags).
+// Where c_split writes.  Planes are [hi | lo], each `*_plane_stride` floats apart, rows zero-padded to Dp floats.
+// The b planes can go to several destinations at once: on one GPU that is the local workspace; across GPUs every
+// destination is the slot of this rank inside a peer's symmetric buffer (NVLink P2P stores), i.e. the all-gather of
+// the text embeddings is fused into this kernel, followed by a release of flags[p][flag_index] = epoch on every peer.
+constexpr int kMaxWorld = 8;
+struct SplitDst {
+    float*    a_planes;
+    size_t    a_plane_stride;
+    float*    b_dst[kMaxWorld];
+    size_t    b_plane_stride;
+    int       n_dst;
+    unsigned* flags[kMaxWorld];     // nullptr entries: no flag protocol (single GPU)
+    int       flag_index;
+    unsigned  epoch;
+    unsigned* counter;              // local: CTAs that have finished their stores
+};
+
+// hi / lo planes of both operands (rows [0, N) = a, [N, N + M) = b).  inv == nullptr: normalise unconditionally
+// with the norm computed here (no separate norm pass, no flags).
 __global__ void __launch_bounds__(256)
 c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, int D, int Dp,
-        const float* __restrict__ inv_a, const float* __restrict__ inv_b, const CosWs* __restrict__ ws,
-        float* __restrict__ a_hi, float* __restrict__ a_lo, float* __restrict__ b_hi, float* __restrict__ b_lo) {
+        const float* __restrict__ inv_a, const float* __restrict__ inv_b, const CosWs* __restrict__ ws, const SplitDst dst) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= N + M) return;
-    const bool is_b = row >= N;
-    if (is_b) row -= N;
-    const float* p = (is_b ? b : a) + (size_t)row * D;
-    float scale;
-    if (inv_a == nullptr) scale = 1.0f / fmaxf(sqrtf(row_sumsq(p, D, lane)), 1e-12f);
-    else scale = (is_b ? ws->flag_b : ws->flag_a) ? (is_b ? inv_b : inv_a)[row] : 1.0f;
-    float* ph = (is_b ? b_hi : a_hi) + (size_t)row * Dp;
-    float* pl = (is_b ? b_lo : a_lo) + (size_t)row * Dp;
-    for (int i = lane; i < Dp; i += 32) {
-        const float v = i < D ? __ldg(p + i) * scale : 0.0f;
-        const float h = __int_as_float(__float_as_int(v) & 0xffffe000);     // TF32: 10 explicit mantissa bits
-        ph[i] = h;
-        pl[i] = v - h;
+    if (row < N + M) {
+        const bool is_b = row >= N;
+        if (is_b) row -= N;
+        const float* p = (is_b ? b : a) + (size_t)row * D;
+        float scale;
+        if (inv_a == nullptr) scale = 1.0f / fmaxf(sqrtf(row_sumsq(p, D, lane)), 1e-12f);
+        else scale = (is_b ? ws->flag_b : ws->flag_a) ? (is_b ? inv_b : inv_a)[row] : 1.0f;
+        const size_t off = (size_t)row * Dp;
+        for (int i = lane; i < Dp; i += 32) {
+            const float v = i < D ? __ldg(p + i) * scale : 0.0f;
+            const float h = __int_as_float(__float_as_int(v) & 0xffffe000);     // TF32: 10 explicit mantissa bits
+            const float l = v - h;
+            if (!is_b) {
+                dst.a_planes[off + i] = h;
+                dst.a_planes[dst.a_plane_stride + off + i] = l;
+            } else {
+#pragma unroll 1
+                for (int d = 0; d < dst.n_dst; ++d) {
+                    dst.b_dst[d][off + i] = h;
+                    dst.b_dst[d][dst.b_plane_stride + off + i] = l;
+                }
+            }
+        }
+    }
+    if (dst.counter) {
+        // publish: every CTA's stores are fenced system-wide, the last CTA releases the flag on every peer
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(dst.counter, 1u);
+            if (done == gridDim.x - 1) {
+                __threadfence_system();
+                for (int d = 0; d < dst.n_dst; ++d)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst.flags[d] + dst.flag_index), "r"(dst.epoch) : "memory");
+                *dst.counter = 0;
+            }
+        }
     }
 }
 
+// Geometry of one launch of c_nxm_tc.  B lives in `world` slots of [hi | lo] planes of b_plane_rows rows each (one slot
+// per source rank; one slot on a single GPU); column tiles are visited in `slot[]` order (own rank first).
+struct TcGeom {
+    int n_rows;                     // valid rows of A
+    int a_plane_rows;               // rows between A's hi and lo planes
+    int b_plane_rows;               // rows per plane of a B slot
+    int world;
+    int tiles_start[kMaxWorld + 1]; // prefix sums of the column tiles per slot, in visiting order
+    int slot[kMaxWorld];            // visiting order -> slot
+    int m_count[kMaxWorld];         // valid rows (output columns) of a slot
+    int col_start[kMaxWorld];       // first output column of a slot
+    int ldS;                        // row pitch of S (total columns)
+    const unsigned* flags;          // flags[slot] reaches `epoch` when the slot's planes have landed (nullptr: local data)
+    unsigned epoch;
+};
+
 __global__ void __launch_bounds__(kTcThreads)
-c_nxm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-         int N, int M, int kb_per_pass, float* __restrict__ S) {
+c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+         const __grid_constant__ TcGeom g, int kb_per_pass, float* __restrict__ S) {
     extern __shared__ unsigned char smem_raw[];
     TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+    const int m0 = blockIdx.y * kTM;
+    int ord = 0;
+    while (ord + 1 < g.world && (int)blockIdx.x >= g.tiles_start[ord + 1]) ++ord;
+    const int slot = g.slot[ord];
+    const int j0 = ((int)blockIdx.x - g.tiles_start[ord]) * kTN;          // first row of the tile inside its slot
+    const int n0 = g.col_start[slot] + j0;                                // first output column
+    const int n_valid = min(kTN, g.m_count[slot] - j0);
+    const int b_row_hi = (slot * 2) * g.b_plane_rows + j0, b_row_lo = b_row_hi + g.b_plane_rows;
+    const int N = g.n_rows, M = g.ldS;
     const int num_kb = 3 * kb_per_pass;
 
     if (warp == 1) {
@@ -204,13 +266,23 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            if (g.flags) {
+                // the slot's planes are written by its source rank over NVLink: acquire its flag, then order the
+                // generic-proxy view before the async-proxy (TMA) reads
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g.flags + slot) : "memory");
+                    if ((int)(v - g.epoch) < 0) __nanosleep(64);
+                } while ((int)(v - g.epoch) < 0);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages, it = kb / kStages;
                 if (it > 0) mbar_wait(&sm.empty[s], (unsigned)(it - 1) & 1u);
                 const int pass = kb / kb_per_pass, k0 = (kb - pass * kb_per_pass) * kTK;
                 mbar_expect_tx(&sm.full[s], kTileABytes + kTileBBytes);
-                tma_load_2d(sm.a[s], pass == 1 ? &map_a_lo : &map_a_hi, k0, m0, &sm.full[s]);
-                tma_load_2d(sm.b[s], pass == 2 ? &map_b_lo : &map_b_hi, k0, n0, &sm.full[s]);
+                tma_load_2d(sm.a[s], &map_a, k0, pass == 1 ? m0 + g.a_plane_rows : m0, &sm.full[s]);
+                tma_load_2d(sm.b[s], &map_b, k0, pass == 2 ? b_row_lo : b_row_hi, &sm.full[s]);
             }
         }
         __syncwarp();
@@ -250,7 +322,7 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < N) {
                 float* dst = S + (size_t)row * M + n0 + c0;
-                if (vec && n0 + c0 + 32 <= M) {
+                if (vec && (n0 & 3) == 0 && c0 + 32 <= n_valid) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -258,7 +330,7 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ C
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j < M) dst[j] = __uint_as_float(r[j]);
+                        if (c0 + j < n_valid) dst[j] = __uint_as_float(r[j]);
                 }
             }
         }
@@ -296,8 +368,28 @@ int make_map(CUtensorMap* map, const float* base, int rows, int Dp, int box_rows
 }
 
 inline int padded_d(int D) { return (D + kTK - 1) / kTK * kTK; }
-
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+int launch_gemm(const float* a_planes, int a_rows_total, const float* b_planes, int b_rows_total, int Dp, const TcGeom& g,
+                int n_col_tiles, float* d_S, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    if (int rc = make_map(&ma, a_planes, a_rows_total, Dp, kTM)) return rc;
+    if (int rc = make_map(&mb, b_planes, b_rows_total, Dp, kTN)) return rc;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    STX_CUDA(cudaGetDevice(&dev));
+    const int smem_bytes = (int)sizeof(TcSmem) + 1024;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STX_CUDA(cudaFuncSetAttribute(c_nxm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set[dev] = true;
+    }
+    STX_LAUNCH(c_nxm_tc, dim3(n_col_tiles, (g.n_rows + kTM - 1) / kTM), dim3(kTcThreads), smem_bytes, st,
+               ma, mb, g, Dp / kTK, d_S);
+    return 0;
+}
+
+// layout of a rank's symmetric buffer for the gathered N x M call: [world][hi | lo][m_cap][Dp] floats, then flags
+inline size_t symm_planes_bytes(int world, int m_cap, int Dp) { return align256(size_t(world) * 2 * m_cap * Dp * sizeof(float)); }
 
 }  // namespace
 }  // namespace stx
@@ -356,28 +448,86 @@ int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int 
     if (int rc = cosine_prepare(d_a, d_b, N, M, D, d_ws, ws_bytes, st, &ws, &inv_a, &inv_b, !always_normalize)) return rc;
     const int Dp = padded_d(D);
     char* p = reinterpret_cast<char*>(inv_b) + align256(size_t(M) * sizeof(float));
-    float* a_hi = reinterpret_cast<float*>(p);  p += align256(size_t(N) * Dp * sizeof(float));
-    float* a_lo = reinterpret_cast<float*>(p);  p += align256(size_t(N) * Dp * sizeof(float));
-    float* b_hi = reinterpret_cast<float*>(p);  p += align256(size_t(M) * Dp * sizeof(float));
-    float* b_lo = reinterpret_cast<float*>(p);
+    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(size_t(N) * Dp * sizeof(float));
+    float* b_planes = reinterpret_cast<float*>(p);
+    SplitDst dst = {};
+    dst.a_planes = a_planes;  dst.a_plane_stride = size_t(N) * Dp;
+    dst.b_dst[0] = b_planes;  dst.b_plane_stride = size_t(M) * Dp;  dst.n_dst = 1;
     STX_LAUNCH(c_split, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
-               always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, a_hi, a_lo, b_hi, b_lo);
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    if (int rc = make_map(&ma_hi, a_hi, N, Dp, kTM)) return rc;
-    if (int rc = make_map(&ma_lo, a_lo, N, Dp, kTM)) return rc;
-    if (int rc = make_map(&mb_hi, b_hi, M, Dp, kTN)) return rc;
-    if (int rc = make_map(&mb_lo, b_lo, M, Dp, kTN)) return rc;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    STX_CUDA(cudaGetDevice(&dev));
-    const int smem_bytes = (int)sizeof(TcSmem) + 1024;
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STX_CUDA(cudaFuncSetAttribute(c_nxm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_set[dev] = true;
+               always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
+    TcGeom g = {};
+    g.n_rows = N;  g.a_plane_rows = N;  g.b_plane_rows = M;  g.world = 1;
+    g.tiles_start[0] = 0;  g.tiles_start[1] = (M + kTN - 1) / kTN;
+    g.slot[0] = 0;  g.m_count[0] = M;  g.col_start[0] = 0;  g.ldS = M;
+    return launch_gemm(a_planes, 2 * N, b_planes, 2 * M, Dp, g, g.tiles_start[1], d_S, st);
+}
+
+int stx_cosine_gather_sizes(int n_local, int m_cap, int world, int D, size_t* ws_bytes, size_t* symm_bytes) {
+    using namespace stx;
+    if (n_local < 0 || m_cap < 0 || world < 1 || world > kMaxWorld || D <= 0 || !ws_bytes || !symm_bytes) {
+        set_error("stx_cosine_gather_sizes: bad argument (1 <= world <= %d)", kMaxWorld);
+        return STX_EINVAL;
     }
-    STX_LAUNCH(c_nxm_tc, dim3((M + kTN - 1) / kTN, (N + kTM - 1) / kTM), dim3(kTcThreads), smem_bytes, st,
-               ma_hi, ma_lo, mb_hi, mb_lo, N, M, Dp / kTK, d_S);
+    const int Dp = padded_d(D);
+    *ws_bytes = 2 * align256(size_t(n_local) * Dp * sizeof(float)) + 256;
+    *symm_bytes = symm_planes_bytes(world, m_cap, Dp) + 256 /* flags */ + 256 /* counter */;
     return 0;
+}
+
+int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int D, int world, int rank,
+                            const int32_t* h_counts, int m_cap, void* const* h_peer_symm, uint32_t epoch,
+                            float* d_S, void* d_ws, size_t ws_bytes, void* stream) {
+    using namespace stx;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_local < 0 || D <= 0 || m_cap <= 0 || !h_counts ||
+        !h_peer_symm) {
+        set_error("stx_cosine_nxm_gathered: bad argument");
+        return STX_EINVAL;
+    }
+    int M = 0;
+    for (int r = 0; r < world; ++r) {
+        if (h_counts[r] < 0 || h_counts[r] > m_cap || !h_peer_symm[r]) { set_error("stx_cosine_nxm_gathered: bad shard %d", r); return STX_EINVAL; }
+        M += h_counts[r];
+    }
+    if (!d_a || !d_b || !d_S || !d_ws) { set_error("stx_cosine_nxm_gathered: null pointer"); return STX_EINVAL; }
+    size_t need = 0, symm = 0;
+    stx_cosine_gather_sizes(n_local, m_cap, world, D, &need, &symm);
+    if (ws_bytes < need) { set_error("stx_cosine_nxm_gathered: workspace %zu < %zu bytes", ws_bytes, need); return STX_ENOSPACE; }
+    if (int rc = check_device()) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Dp = padded_d(D);
+    const size_t planes = symm_planes_bytes(world, m_cap, Dp);
+    const size_t slot_floats = size_t(2) * m_cap * Dp;
+    float* a_planes = static_cast<float*>(d_ws);
+    SplitDst dst = {};
+    dst.a_planes = a_planes;  dst.a_plane_stride = size_t(n_local) * Dp;
+    dst.b_plane_stride = size_t(m_cap) * Dp;  dst.n_dst = world;
+    for (int p = 0; p < world; ++p) {
+        char* base = static_cast<char*>(h_peer_symm[p]);
+        dst.b_dst[p] = reinterpret_cast<float*>(base) + size_t(rank) * slot_floats;       // my slot in peer p's buffer
+        dst.flags[p] = reinterpret_cast<unsigned*>(base + planes);
+    }
+    char* mine = static_cast<char*>(h_peer_symm[rank]);
+    dst.flag_index = rank;  dst.epoch = epoch;
+    dst.counter = reinterpret_cast<unsigned*>(mine + planes + 256);
+    // normalise + split + all-gather over NVLink (P2P stores into every peer's slot) in one kernel
+    STX_LAUNCH(c_split, dim3((n_local + h_counts[rank] + 7) / 8), dim3(256), 0, st, d_a, d_b, n_local, h_counts[rank], D, Dp,
+               nullptr, nullptr, nullptr, dst);
+    if (n_local == 0 || M == 0) return 0;
+    TcGeom g = {};
+    g.n_rows = n_local;  g.a_plane_rows = n_local;  g.b_plane_rows = m_cap;  g.world = world;  g.ldS = M;
+    int col = 0;
+    for (int r = 0; r < world; ++r) { g.m_count[r] = h_counts[r]; g.col_start[r] = col; col += h_counts[r]; }
+    int tiles = 0;
+    for (int o = 0; o < world; ++o) {           // own columns first, then ring order: early CTAs never wait
+        const int slot = (rank + o) % world;
+        g.slot[o] = slot;
+        g.tiles_start[o] = tiles;
+        tiles += (h_counts[slot] + kTN - 1) / kTN;
+    }
+    for (int o = world; o <= kMaxWorld; ++o) g.tiles_start[o] = tiles;
+    g.flags = reinterpret_cast<const unsigned*>(mine + planes);
+    g.epoch = epoch;
+    return launch_gemm(a_planes, 2 * n_local, reinterpret_cast<const float*>(mine), world * 2 * m_cap, Dp, g, tiles, d_S, st);
 }
 
 }  // extern "C"

@@ -1,7 +1,8 @@
 """cfg5: inference-style scoring, N = M = 4096 embedding pairs, all-gathered N x M cosine matrix.
 
     python tools/bench_cosine.py                       # 1 GPU: full 4096 x 4096 matrix
-    torchrun --nproc-per-node 8 tools/bench_cosine.py  # 8 GPUs: [512, D] shards, NCCL all-gather, [512, 4096] stripes
+    torchrun --nproc-per-node 8 tools/bench_cosine.py  # 8 GPUs: [512, D] shards, all-gather fused into the kernels
+                                                       # over NVLink peer memory, [512, 4096] stripes
 
 Prints one JSON line per D in {768, 1024}: time (CUDA events, max over ranks), TFLOP/s, GB/s, max-abs error vs
 the float64 oracle on a sample of rows (checker only).
@@ -35,9 +36,12 @@ for D in (768, 1024):
     a_loc = torch.from_numpy(a[lo:hi]).to(dev)
     b_loc = torch.from_numpy(b[lo:hi]).to(dev)
 
+    counts = [scoring.shard_rows(M, world, r)[1] - scoring.shard_rows(M, world, r)[0] for r in range(world)]
+    scorer = scoring.GatheredScorer(max(counts), D, device=dev) if world > 1 else None
+
     def step():
         if world > 1:
-            return scoring.sharded_cosine_matrix(a_loc, b_loc)
+            return scorer(a_loc, b_loc, counts=counts)          # all-gather fused into the kernels over NVLink
         return scoring.cosine_matrix(a_loc, b_loc)
 
     for _ in range(warm):
@@ -57,6 +61,20 @@ for D in (768, 1024):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    ms_nccl = None
+    if world > 1:                                               # the baseline: NCCL all-gather, then the local kernel
+        for _ in range(warm):
+            scoring.sharded_cosine_matrix(a_loc, b_loc, counts=counts)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            scoring.sharded_cosine_matrix(a_loc, b_loc, counts=counts)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_nccl = float(t.item())
     ref = OC.matrix_f64(a[lo:lo + 64], b)
     err = float(np.abs(S[:64].cpu().numpy() - ref).max())
     if rank == 0:
@@ -64,7 +82,7 @@ for D in (768, 1024):
         byts = 4.0 * (N * D + M * D + N * M)
         print(json.dumps({"workload": f"cfg5 cosine N=M={N} D={D}", "n_gpus": world, "ms": ms,
                           "tflops": flop / ms / 1e9, "gbs": byts / ms / 1e6, "max_abs_err_vs_f64": err,
-                          "kernel_launches_per_call": launches / iters,
+                          "kernel_launches_per_call": launches / iters, "ms_nccl_allgather_then_gemm": ms_nccl,
                           "scores_per_s": N * M / (ms * 1e-3)}), flush=True)
 if world > 1:
     dist.destroy_process_group()
