@@ -29,3 +29,29 @@ def unshard(parts: list[np.ndarray], shards: list[np.ndarray]) -> np.ndarray:
     for p, s in zip(parts, shards):
         out[s] = p
     return out
+
+
+def bind_to_gpu_cpus(device_index: int) -> dict:
+    """Pin the calling process to the CPUs NVML reports as closest to the GPU (its NUMA node), so that the pinned
+    staging buffers allocated afterwards sit on that node and H2D/D2H copies do not cross the socket interconnect.
+    One process per GPU: call it before the first pinned allocation.  Returns what was done (for logs); never
+    raises — without NVML or affinity support the process is left as it is."""
+    import os
+    info = {"device": int(device_index), "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+        info["cpus"] = len(allowed)
+    except Exception as e:                                    # noqa: BLE001 (best effort by design)
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

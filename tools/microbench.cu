@@ -3,6 +3,7 @@
 // Prints lane-operations per clock per SM for each instruction class.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include "../speech_transcript_embeddings_b200/csrc/codelets.cuh"
 
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
 
@@ -145,6 +146,38 @@ static float time_ms(F launch) {
     return ms;
 }
 
+// The generated codelets on register data only (no memory): how close does the compiler's schedule of the
+// straight-line FP64 code get to the pipe's peak with 16 warps per SM and <= 128 registers (the k_frames budget)?
+template <int kWhich>
+__global__ void __launch_bounds__(512, 1) k_codelet(double* out, double seed, int iters) {
+    using namespace stx::codelets;
+    double y[25], re[17], im[17];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) y[i] = seed * (threadIdx.x + i);
+#pragma unroll
+    for (int i = 0; i < 17; ++i) re[i] = im[i] = 0.0;
+    double xr[16], xi[16], yr[16], yi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { xr[i] = seed * i; xi[i] = seed + i; }
+    for (int it = 0; it < iters; ++it) {
+        if (kWhich == 0) {
+            k_pass1<double>(y, re, im);
+#pragma unroll
+            for (int i = 0; i < 25; ++i) y[i] = re[i % 17] * 0.5 + (i < 15 ? im[1 + i] : y[i]) * 0.25;   // +50 ops, keeps everything live
+        } else {
+            dft16<double>(xr, xi, yr, yi);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { xr[i] = yr[i] * 0.5; xi[i] = yi[i] * 0.5; }                  // +32 ops
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) s += y[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += xr[i] + xi[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     cudaDeviceProp p;
     CHECK(cudaGetDeviceProperties(&p, 0));
@@ -177,6 +210,20 @@ int main() {
     report("LDS.64 idx=lane&15", time_ms([&] { k_lds_dup<float2, 1><<<blocks, threads>>>((float*)out); }), 1);
     report("LDS.64 idx=lane>>1", time_ms([&] { k_lds_dup<float2, 2><<<blocks, threads>>>((float*)out); }), 1);
     report("LDS.32 idx=lane&15", time_ms([&] { k_lds_dup<float, 1><<<blocks, threads>>>((float*)out); }), 1);
+    {
+        // ops per iteration from tools/gen_codelets.py (after FMA contraction) + the feedback ops above
+        const int it = 2000, cb = p.multiProcessorCount, ct = 512;
+        void* o2;
+        CHECK(cudaMalloc(&o2, size_t(cb) * ct * 8));
+        const double l2 = double(cb) * ct * it;
+        auto rep2 = [&](const char* name, float ms, double ops) {
+            double ops_per_s = l2 * ops / (ms * 1e-3);
+            printf("%-22s %8.3f ms  %8.2f Tops/s  %7.1f lane-ops/clk/SM @%.0f MHz (attr clock)\n", name, ms, ops_per_s / 1e12,
+                   ops_per_s / p.multiProcessorCount / (clk_khz * 1e3), clk_khz / 1e3);
+        };
+        rep2("codelet k_pass1 f64", time_ms([&] { k_codelet<0><<<cb, ct>>>((double*)o2, 1e-3, it); }), 225 + 50);
+        rep2("codelet dft16 f64", time_ms([&] { k_codelet<1><<<cb, ct>>>((double*)o2, 1e-3, it); }), 176 + 32);
+    }
     CHECK(cudaDeviceSynchronize());
     CHECK(cudaGetLastError());
     return 0;
