@@ -172,6 +172,18 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     for (int t0 = t_begin; t0 < t_end; t0 += kTile) {
         // ---- layout: zero padding to n_samples, reflect padding of 200 around it, peak divisor; rows of 161 ----
         const int g0 = t0 * kHop - kN / 2;
+        if (g0 >= len && len <= n_samples - (kN / 2 + 2)) {
+            // the whole tile lies in the zero padding behind the clip (and the reflected tail of the padded signal is
+            // zero as well): every mel energy is 0, so every value is log10 of the floor; no copy was issued for it
+            const float v = log10f(1e-10f);
+            const int t = t0 + lane;
+            if (t < t_end) {
+#pragma unroll
+                for (int i = 0; i < 5; ++i) out_b[(size_t)(warp + 16 * i) * T + t] = v;
+                run_max = fmaxf(run_max, v);
+            }
+            continue;
+        }
         const StageRange sr = stage_range(g0, len, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {

@@ -206,3 +206,29 @@ def test_trainer_collate_fused(cuda_device, padding_value):
     host = fe.collate(clips, output="host")
     assert host["input_values"].is_pinned() and torch.equal(host["input_values"], got["input_values"].cpu())
     assert torch.equal(host["attention_mask_audio"], got["attention_mask_audio"].cpu())
+
+
+def test_cfg3_variable_length_batch_512(fe):
+    """BASELINE configs[2]: 512 clips of 1-30 s (whole seconds, and an arbitrary-length variant with odd T): shapes,
+    every mask row exact, padding rows exact, oracle on a sample of clips, batch invariance."""
+    for whole in (True, False):
+        clips = synth.batch_variable(512, seed=1234, whole_seconds=whole)
+        got = fe(clips, sampling_rate=16000, return_tensors="pt")
+        x, m = got["input_features"], got["attention_mask"]
+        frames = np.array([ops.k_num_frames(c.size) for c in clips])
+        T_pad = int(frames.max() + (frames.max() & 1))
+        assert tuple(x.shape) == (512, T_pad // 2, 160) and tuple(m.shape) == (512, T_pad // 2)
+        want_mask = (2 * np.arange(T_pad // 2)[None, :] + 1 < frames[:, None]).astype(np.int32)
+        assert np.array_equal(m.cpu().numpy(), want_mask)
+        raw = x.reshape(512, T_pad, 80)
+        worst = 0.0
+        for i in (0, 101, 257, 388, 511, int(np.argmin(frames)), int(np.argmax(frames))):
+            assert not raw[i, frames[i]:].any()                               # padding_value = 0 rows past the clip
+            with np.errstate(all="ignore"):
+                ref = OK.extract([clips[i]])[0][0]
+            mine = x[i, :ref.shape[0]].cpu().numpy()
+            worst = max(worst, float(np.abs(mine - ref).max()))
+            alone = fe(clips[i], sampling_rate=16000, return_tensors="pt")["input_features"][0]
+            assert torch.equal(alone, x[i, :alone.shape[0]])                  # a clip does not depend on its batch
+        print(f"K cfg3 ({'whole seconds' if whole else 'arbitrary lengths'}) sample of 7 clips: max-abs {worst:.2e}")
+        assert worst <= TOL
