@@ -232,3 +232,30 @@ def test_cfg3_variable_length_batch_512(fe):
             assert torch.equal(alone, x[i, :alone.shape[0]])                  # a clip does not depend on its batch
         print(f"K cfg3 ({'whole seconds' if whole else 'arbitrary lengths'}) sample of 7 clips: max-abs {worst:.2e}")
         assert worst <= TOL
+
+
+def test_unaligned_clip_starts_take_the_plain_load_path(cuda_device):
+    """Clips that do not start on a 16-byte boundary cannot be staged by the bulk copy: same bits as the aligned path."""
+    clips = [synth.clip("G", 20000, 1), synth.clip("AM", 7777, 2), synth.clip("U", 16160, 3)]
+    lens = np.array([c.size for c in clips], np.int32)
+    T_pad = 2 * ((max(ops.k_num_frames(int(n)) for n in lens) + 1) // 2)
+
+    def run(lead, gap):
+        offs, pos = [], lead
+        for c in clips:
+            offs.append(pos)
+            pos += c.size + gap
+        buf = np.zeros(pos + 8, np.float32)
+        for c, o in zip(clips, offs):
+            buf[o:o + c.size] = c
+        x, m = ops.fbank_k(torch.from_numpy(buf).to(cuda_device), torch.tensor(offs, dtype=torch.int64, device=cuda_device),
+                           torch.from_numpy(lens).to(cuda_device), int(lens.max()), T_pad)
+        return x.cpu(), m.cpu()
+
+    x0, m0 = run(0, 3)            # offsets 0, 20003, 27783: the 2nd and 3rd clip are unaligned
+    for lead, gap in ((1, 0), (2, 1), (3, 7)):
+        x, m = run(lead, gap)
+        assert torch.equal(x, x0) and torch.equal(m, m0)
+    with np.errstate(all="ignore"):
+        ref_x, ref_m = OK.extract(clips)
+    assert np.abs(x0.numpy() - ref_x).max() <= TOL and np.array_equal(m0.numpy(), ref_m)

@@ -75,3 +75,27 @@ def test_host_output_pipeline_is_bit_identical(cuda_device):
         assert torch.equal(host["attention_mask"], dev_out["attention_mask"].cpu())
     finally:
         type(fe).CHUNK_BYTES = old
+
+
+def test_unaligned_clip_starts_take_the_plain_load_path(cuda_device):
+    from speech_transcript_embeddings_b200 import ops
+    clips = [synth.clip("G", 16000, 1), synth.clip("AM", 9001, 2), synth.clip("U", 12345, 3)]
+    lens = np.array([c.size for c in clips], np.int32)
+
+    def run(lead, gap):
+        offs, pos = [], lead
+        for c in clips:
+            offs.append(pos)
+            pos += c.size + gap
+        buf = np.zeros(pos + 8, np.float32)
+        for c, o in zip(clips, offs):
+            buf[o:o + c.size] = c
+        x, _ = ops.logmel_w(torch.from_numpy(buf).to(cuda_device), torch.tensor(offs, dtype=torch.int64, device=cuda_device),
+                            torch.from_numpy(lens).to(cuda_device), 16000)
+        return x.cpu()
+
+    x0 = run(0, 3)
+    for lead, gap in ((1, 0), (2, 1), (3, 7)):
+        assert torch.equal(run(lead, gap), x0)
+    ref, _ = OW.extract(clips, n_samples=16000)
+    assert np.abs(x0.numpy() - ref).max() <= TOL
