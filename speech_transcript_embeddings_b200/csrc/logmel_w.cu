@@ -120,21 +120,20 @@ __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const fl
     return log10f(fmaxf(acc0 + acc1, 1e-10f));
 }
 
-// float max through integer atomics (works for any sign, destination initialised to -inf)
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+// Per-clip max through an order-preserving integer key (negative floats: all bits flipped, others: sign bit set), so
+// that key 0 is below every float and a plain memset initialises the maxima (no init kernel).
+__device__ __forceinline__ unsigned max_key(float v) {
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
-
-__global__ void w_init_max(float* __restrict__ clip_max, int B) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) clip_max[i] = __int_as_float(0xff800000);
+__device__ __forceinline__ float max_unkey(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
          const float* __restrict__ peaks, const WTables* __restrict__ tab, int n_samples, int chunk_frames,
-         float* __restrict__ out, float* __restrict__ clip_max) {
+         float* __restrict__ out, unsigned* __restrict__ clip_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -284,17 +283,17 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         float m = sm.wmax[0];
 #pragma unroll
         for (int w = 1; w < kWarps; ++w) m = fmaxf(m, sm.wmax[w]);
-        atomic_max_float(clip_max + b, m);
+        atomicMax(clip_max + b, max_key(m));
     }
 }
 
 // max(x, max - 8), (x + 4) / 4 in place; mask[b, j] = (160 j < len)
 __global__ void __launch_bounds__(256)
-w_finish(const int* __restrict__ lengths, const float* __restrict__ clip_max, int n_samples,
+w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max, int n_samples,
          float* __restrict__ out, int* __restrict__ mask) {
     const int b = blockIdx.y;
     const int T = n_samples / kHop;
-    const float lo = clip_max[b] - 8.0f;
+    const float lo = max_unkey(clip_max[b]) - 8.0f;
     const size_t total = (size_t)kMel * T;
     float* o = out + (size_t)b * total;
     const bool vec = (total % 4 == 0);
@@ -403,9 +402,9 @@ int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_
     const WTables* tab = nullptr;
     if (int rc = get_tables(&tab)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float* clip_max = static_cast<float*>(d_ws);
+    unsigned* clip_max = static_cast<unsigned*>(d_ws);
     const int T = n_samples / kHop;
-    STX_LAUNCH(w_init_max, dim3((B + 255) / 256), dim3(256), 0, st, clip_max, B);
+    STX_CUDA(cudaMemsetAsync(clip_max, 0, size_t(B) * sizeof(unsigned), st));
     static int sms = 0;
     if (!sms) {
         int dev = 0;
