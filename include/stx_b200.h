@@ -146,6 +146,20 @@ int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int 
                    float* d_S, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Evaluation-time consumers of the pairwise scores, fused into one pass over the embeddings (forward only).
+ * Replaces, for one batch of [B, D] audio / clean-transcript / corrupted-transcript embeddings:
+ *   F.normalize x3 + s_pos, s_neg = (aud * txt).sum(dim=1)     R/training/trainer_unfreeze.py:561-563, 1206-1207
+ *   to_human_readable(s, temperature, "prob") = sigmoid(s / t)  R/training/trainer_unfreeze.py:924-939, 1215-1216
+ *   AlignmentAwareInfoNCE.forward                               R/training/trainer_unfreeze.py:716-741:
+ *     per_sample = CE([s_pos, s_neg] / t, target 0) * (d_align_factor[b] if given: 1 - sigmoid(mean_align) * w)
+ *     loss       = mean(per_sample) + corrupt_gamma * mean(relu(s_neg))        (corrupt_gamma <= 0: no penalty)
+ * All outputs float32: five [B] vectors and the scalar d_loss.
+ * ------------------------------------------------------------------------------------------- */
+int stx_score_pos_neg(const float* d_aud, const float* d_pos, const float* d_neg, int B, int D, float temperature,
+                      float corrupt_gamma, const float* d_align_factor, float* d_s_pos, float* d_s_neg,
+                      float* d_hr_pos, float* d_hr_neg, float* d_per_sample, float* d_loss, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU N x M scoring: this rank's stripe S[rows of a, all M] where the text embeddings b are sharded over
  * `world` ranks of one NVLink/NVSwitch box (BASELINE.json configs[4]).  The reference has no collective; this is the
  * north_star's "all-gathered N x M cosine matrix".  The all-gather is FUSED into the kernels over peer memory:

@@ -43,3 +43,24 @@ def pairwise_f64(e1: np.ndarray, e2: np.ndarray) -> np.ndarray:
 
 def matrix_f64(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     return l2_normalize(a) @ l2_normalize(b).T
+
+
+def pos_neg_reference(aud: np.ndarray, pos: np.ndarray, neg: np.ndarray, temperature: float = 0.1,
+                      corrupt_gamma: float = 0.35, alignment_factor: np.ndarray | None = None) -> dict:
+    """The evaluation-time scoring consumers, float64:
+      s_pos / s_neg     (aud * txt).sum(dim=1) after F.normalize      R/training/trainer_unfreeze.py:561-563, 1206-1207
+      hr_pos / hr_neg   to_human_readable(s, temperature, "prob") = sigmoid(s / temperature)      :924-939, 1215-1216
+      per_sample        F.cross_entropy(stack([s_pos, s_neg], 1) / temperature, target 0, reduction="none")  :722-726
+                        times the optional alignment factor 1 - sigmoid(mean_align) * alignment_weight      :729-733
+      loss              per_sample.mean() + corrupt_gamma * relu(s_neg).mean()                    :735-739
+    """
+    a, p, n = l2_normalize(aud), l2_normalize(pos), l2_normalize(neg)
+    s_pos, s_neg = (a * p).sum(axis=1), (a * n).sum(axis=1)
+    z = (s_neg - s_pos) / temperature
+    per = np.logaddexp(0.0, z)                                  # log(1 + exp(l_neg - l_pos))
+    if alignment_factor is not None:
+        per = per * np.asarray(alignment_factor, np.float64)
+    loss = per.mean() + (corrupt_gamma * np.maximum(s_neg, 0.0).mean() if corrupt_gamma > 0 else 0.0)
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    return {"s_pos": s_pos, "s_neg": s_neg, "hr_pos": sig(s_pos / temperature), "hr_neg": sig(s_neg / temperature),
+            "per_sample": per, "loss": float(loss)}

@@ -84,6 +84,58 @@ c_pairwise(const float* __restrict__ a, const float* __restrict__ b, int N, int 
     }
 }
 
+// ---- the evaluation-time consumers of the pairwise scores, fused ---------------------------
+// One warp per item: s_pos = <aud, pos>, s_neg = <aud, neg> after F.normalize (R/training/trainer_unfreeze.py:561-563,
+// 1206-1207), hr = sigmoid(s / temperature) (to_human_readable, :924-939), per-sample 2-way InfoNCE
+// CE([s_pos, s_neg] / temperature, 0) = softplus((s_neg - s_pos) / temperature) times an optional alignment factor
+// (:722-733); c_pos_neg_loss: mean(per-sample) + gamma * mean(relu(s_neg)) (:735-739), one CTA, fixed summation order.
+struct PosNegOut { float *s_pos, *s_neg, *hr_pos, *hr_neg, *per_sample; };
+
+__global__ void __launch_bounds__(256)
+c_pos_neg(const float* __restrict__ aud, const float* __restrict__ pos, const float* __restrict__ neg, int B, int D,
+          float inv_temperature, const float* __restrict__ align_factor, const PosNegOut o) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float* pa = aud + (size_t)row * D;
+    const float* pp = pos + (size_t)row * D;
+    const float* pn = neg + (size_t)row * D;
+    float aa = 0.0f, bb = 0.0f, cc = 0.0f, ab = 0.0f, ac = 0.0f;
+    for (int i = lane; i < D; i += 32) {
+        const float a = __ldg(pa + i), b = __ldg(pp + i), c = __ldg(pn + i);
+        aa = fmaf(a, a, aa); bb = fmaf(b, b, bb); cc = fmaf(c, c, cc);
+        ab = fmaf(a, b, ab); ac = fmaf(a, c, ac);
+    }
+    aa = warp_sum(aa); bb = warp_sum(bb); cc = warp_sum(cc); ab = warp_sum(ab); ac = warp_sum(ac);
+    if (lane == 0) {
+        const float ia = 1.0f / fmaxf(sqrtf(aa), 1e-12f);
+        const float s_pos = ab * ia * (1.0f / fmaxf(sqrtf(bb), 1e-12f));
+        const float s_neg = ac * ia * (1.0f / fmaxf(sqrtf(cc), 1e-12f));
+        const float z = (s_neg - s_pos) * inv_temperature;
+        float per = fmaxf(z, 0.0f) + log1pf(expf(-fabsf(z)));          // softplus, stable
+        if (align_factor) per *= align_factor[row];
+        o.s_pos[row] = s_pos;
+        o.s_neg[row] = s_neg;
+        o.hr_pos[row] = 1.0f / (1.0f + expf(-s_pos * inv_temperature));
+        o.hr_neg[row] = 1.0f / (1.0f + expf(-s_neg * inv_temperature));
+        o.per_sample[row] = per;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+c_pos_neg_loss(const float* __restrict__ per_sample, const float* __restrict__ s_neg, int B, float gamma, float* __restrict__ loss) {
+    __shared__ double red[2][256];
+    double a = 0.0, r = 0.0;
+    for (int i = threadIdx.x; i < B; i += 256) { a += (double)per_sample[i]; r += (double)fmaxf(s_neg[i], 0.0f); }
+    red[0][threadIdx.x] = a; red[1][threadIdx.x] = r;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss = (float)(red[0][0] / B + (gamma > 0.0f ? (double)gamma * red[1][0] / B : 0.0));
+}
+
 // ---- N x M contraction on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) -------------------
 //
 // float32 accuracy from TF32 MMAs by operand splitting: x = hi + lo with hi = x truncated to TF32 (exactly
@@ -460,6 +512,24 @@ int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int 
     g.tiles_start[0] = 0;  g.tiles_start[1] = (M + kTN - 1) / kTN;
     g.slot[0] = 0;  g.m_count[0] = M;  g.col_start[0] = 0;  g.ldS = M;
     return launch_gemm(a_planes, 2 * N, b_planes, 2 * M, Dp, g, g.tiles_start[1], d_S, st);
+}
+
+int stx_score_pos_neg(const float* d_aud, const float* d_pos, const float* d_neg, int B, int D, float temperature,
+                      float corrupt_gamma, const float* d_align_factor, float* d_s_pos, float* d_s_neg, float* d_hr_pos,
+                      float* d_hr_neg, float* d_per_sample, float* d_loss, void* stream) {
+    using namespace stx;
+    if (B < 0 || D <= 0 || !(temperature > 0.0f)) { set_error("stx_score_pos_neg: need B >= 0, D > 0, temperature > 0"); return STX_EINVAL; }
+    if (B == 0) return 0;
+    if (!d_aud || !d_pos || !d_neg || !d_s_pos || !d_s_neg || !d_hr_pos || !d_hr_neg || !d_per_sample || !d_loss) {
+        set_error("stx_score_pos_neg: null pointer");
+        return STX_EINVAL;
+    }
+    if (int rc = check_device()) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const PosNegOut o = {d_s_pos, d_s_neg, d_hr_pos, d_hr_neg, d_per_sample};
+    STX_LAUNCH(c_pos_neg, dim3((B + 7) / 8), dim3(256), 0, st, d_aud, d_pos, d_neg, B, D, 1.0f / temperature, d_align_factor, o);
+    STX_LAUNCH(c_pos_neg_loss, dim3(1), dim3(256), 0, st, d_per_sample, d_s_neg, B, corrupt_gamma, d_loss);
+    return 0;
 }
 
 int stx_cosine_gather_sizes(int n_local, int m_cap, int world, int D, size_t* ws_bytes, size_t* symm_bytes) {

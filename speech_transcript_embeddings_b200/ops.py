@@ -207,3 +207,31 @@ def cosine_nxm(a: torch.Tensor, b: torch.Tensor, always_normalize: bool = True,
                                       out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(a.device)),
                    "stx_cosine_nxm")
     return out
+
+
+def score_pos_neg(aud: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, temperature: float = 0.1,
+                  corrupt_gamma: float = 0.35, alignment_factor: torch.Tensor | None = None) -> dict:
+    """Evaluation-time scoring of a batch (R/training/trainer_unfreeze.py:1206-1216, 716-741), forward only:
+    ``s_pos``, ``s_neg``, ``hr_pos``, ``hr_neg`` (sigmoid(s / temperature)), ``per_sample`` (2-way InfoNCE) as
+    float32 [B] and the scalar ``loss``, all on the GPU."""
+    lib = _lib.load()
+    for name, t in (("aud", aud), ("pos", pos), ("neg", neg)):
+        _require_cuda(t, name, torch.float32)
+    if aud.dim() != 2 or aud.shape != pos.shape or aud.shape != neg.shape:
+        raise ValueError("expected three [B, D] tensors of equal shape")
+    if alignment_factor is not None:
+        _require_cuda(alignment_factor, "alignment_factor", torch.float32)
+        if alignment_factor.shape != (aud.shape[0],):
+            raise ValueError("alignment_factor must be [B]")
+    B, D = aud.shape
+    dev = aud.device
+    out = {k: torch.empty(B, dtype=torch.float32, device=dev) for k in ("s_pos", "s_neg", "hr_pos", "hr_neg", "per_sample")}
+    out["loss"] = torch.zeros((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_score_pos_neg(aud.data_ptr(), pos.data_ptr(), neg.data_ptr(), B, D, float(temperature),
+                                         float(corrupt_gamma),
+                                         alignment_factor.data_ptr() if alignment_factor is not None else None,
+                                         out["s_pos"].data_ptr(), out["s_neg"].data_ptr(), out["hr_pos"].data_ptr(),
+                                         out["hr_neg"].data_ptr(), out["per_sample"].data_ptr(), out["loss"].data_ptr(),
+                                         _stream_ptr(dev)), "stx_score_pos_neg")
+    return out

@@ -63,3 +63,33 @@ def test_zero_rows_do_not_produce_nans(cuda_device):
     b = np.ones((4, 32), np.float32)
     got = ops.cosine_pairwise(_dev(a, cuda_device), _dev(b, cuda_device)).cpu().numpy()
     assert np.array_equal(got, np.zeros(4, np.float32))     # x / max(|x|, 1e-12) = 0, like F.normalize
+
+
+def test_pos_neg_scoring_consumers(cuda_device):
+    """sigmoid(cos / t), the 2-way InfoNCE and its corrupt penalty (R/training/trainer_unfreeze.py:716-741, 924-939),
+    checked against the float64 oracle and against torch's own float32 ops on the CPU (the reference's arithmetic)."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(5)
+    for B, D in ((8, 768), (257, 1024), (1, 7)):
+        aud, pos = synth.embedding_pairs(B, D, seed=B)
+        neg = (pos + 0.8 * rng.standard_normal((B, D))).astype(np.float32) * np.float32(2.5)      # not normalised
+        fac = (1.0 - 0.3 / (1.0 + np.exp(-rng.standard_normal(B)))).astype(np.float32)
+        for gamma, factor in ((0.35, None), (0.0, fac)):
+            got = ops.score_pos_neg(_dev(aud, cuda_device), _dev(pos, cuda_device), _dev(neg, cuda_device), 0.1, gamma,
+                                    _dev(factor, cuda_device) if factor is not None else None)
+            ref = OC.pos_neg_reference(aud, pos, neg, 0.1, gamma, factor)
+            for k in ("s_pos", "s_neg"):
+                assert np.abs(got[k].cpu().numpy() - ref[k]).max() <= TOL
+            for k in ("hr_pos", "hr_neg"):
+                assert np.abs(got[k].cpu().numpy() - ref[k]).max() <= 2e-5          # sigmoid(s / 0.1): slope <= 2.5
+            assert np.abs(got["per_sample"].cpu().numpy() - ref["per_sample"]).max() <= 1e-4   # d/ds <= 10
+            assert abs(float(got["loss"]) - ref["loss"]) <= 1e-4
+            # the reference's own torch ops (CPU, float32)
+            ta, tp, tn = (F.normalize(torch.from_numpy(x), p=2, dim=1) for x in (aud, pos, neg))
+            s_pos, s_neg = (ta * tp).sum(1), (ta * tn).sum(1)
+            per = F.cross_entropy(torch.stack([s_pos, s_neg], 1) / 0.1, torch.zeros(B, dtype=torch.long), reduction="none")
+            if factor is not None:
+                per = per * torch.from_numpy(factor)
+            loss = per.mean() + (gamma * F.relu(s_neg).mean() if gamma > 0 else 0.0)
+            assert abs(float(got["loss"]) - float(loss)) <= 1e-4
+            assert (got["hr_pos"].cpu() - torch.sigmoid(s_pos / 0.1)).abs().max().item() <= 2e-5

@@ -94,3 +94,29 @@ def test_library_tables_match_oracle_tables(lib):
     k = OK.kaldi_mel_filters()
     assert (k != 0).sum() == 501 and not k[0].any() and not k[256].any()
     assert (OW.slaney_mel_filters() != 0).sum() == 391
+
+
+def test_pos_neg_oracle_matches_the_references_torch_ops():
+    """oracle.cosine.pos_neg_reference vs the statements of R/training/trainer_unfreeze.py:561-563, 716-741, 924-939
+    executed with torch on the CPU (float64)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import cosine as OC
+    from speech_transcript_embeddings_b200 import synth
+    aud, pos = synth.embedding_pairs(33, 96, seed=2)
+    neg = pos[::-1].copy() * np.float32(1.7)
+    fac = np.linspace(0.7, 1.0, 33)
+    for gamma, factor in ((0.35, None), (0.0, fac)):
+        ref = OC.pos_neg_reference(aud, pos, neg, 0.1, gamma, factor)
+        ta, tp, tn = (F.normalize(torch.from_numpy(x).double(), p=2, dim=1) for x in (aud, pos, neg))
+        s_pos, s_neg = (ta * tp).sum(1), (ta * tn).sum(1)
+        logits = torch.stack([s_pos, s_neg], 1) / 0.1
+        per = F.cross_entropy(logits, torch.zeros(33, dtype=torch.long), reduction="none")
+        if factor is not None:
+            per = per * torch.from_numpy(factor)
+        loss = per.mean()
+        if gamma > 0:
+            loss = loss + gamma * F.relu(s_neg).mean()
+        assert np.abs(ref["s_pos"] - s_pos.numpy()).max() < 1e-14 and np.abs(ref["per_sample"] - per.numpy()).max() < 1e-12
+        assert abs(ref["loss"] - float(loss)) < 1e-12
+        assert np.abs(ref["hr_neg"] - torch.sigmoid(s_neg / 0.1).numpy()).max() < 1e-14
