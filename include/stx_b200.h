@@ -169,15 +169,19 @@ int stx_score_pos_neg(const float* d_aud, const float* d_pos, const float* d_neg
  *     P2P stores over NVLink and then releases flag[rank] = epoch on every peer;
  *   - the tcgen05 GEMM visits its own columns first and, per source rank, acquires that rank's flag before the
  *     first TMA load of its columns, so the math on arrived shards overlaps the transfers still in flight.
- * `epoch` must increase by 1 per call on all ranks (start at 1; the buffer must be zeroed once after allocation),
- * and the caller must keep a cross-rank barrier between the end of one call and the start of the next (a rank
- * must not overwrite a slot that a peer is still reading).  h_counts[r] = rows of rank r's shard (<= m_cap).
+ * `epoch` must increase by 1 per call on all ranks (start at 1; the buffer must be zeroed once after allocation and
+ * before any rank's first call).  The buffer holds two sets of planes + flags used alternately by epoch parity, so
+ * no cross-rank barrier is needed between calls: a rank's push of call e+2 follows its GEMM of call e+1 in stream
+ * order, and that GEMM has acquired every peer's e+1 flag, which the peer published after its own GEMM of call e.
+ * h_counts[r] = rows of rank r's shard (<= m_cap).
+ * d_multicast: NULL, or the NVSwitch multicast address of the same symmetric buffer (one `multimem.st` then reaches
+ * every peer's copy instead of `world` unicast stores).
  * d_S is [n_local, sum(h_counts)] float32.  Rows are always L2-normalised.
  * ------------------------------------------------------------------------------------------- */
 int stx_cosine_gather_sizes(int n_local, int m_cap, int world, int D, size_t* ws_bytes, size_t* symm_bytes);
 int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int D, int world, int rank,
-                            const int32_t* h_counts, int m_cap, void* const* h_peer_symm, uint32_t epoch,
-                            float* d_S, void* d_ws, size_t ws_bytes, void* stream);
+                            const int32_t* h_counts, int m_cap, void* const* h_peer_symm, void* d_multicast,
+                            uint32_t epoch, float* d_S, void* d_ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

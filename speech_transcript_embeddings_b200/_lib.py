@@ -38,8 +38,8 @@ _SIGNATURES = {
     "stx_cosine_gather_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t),
                                           C.POINTER(C.c_size_t)]),
     "stx_cosine_nxm_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                          C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
-                                          C.c_void_p]),
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -210,6 +210,8 @@ constexpr int kMaxWorld = 8;
 struct SplitDst {
     float*    a_planes;
     size_t    a_plane_stride;
+    float*    b_mc;                 // NVSwitch multicast address of this rank's slot (one multimem.st reaches every
+                                    // peer), or nullptr: unicast P2P stores to b_dst[0 .. n_dst)
     float*    b_dst[kMaxWorld];
     size_t    b_plane_stride;
     int       n_dst;
@@ -234,18 +236,35 @@ c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, 
         if (inv_a == nullptr) scale = 1.0f / fmaxf(sqrtf(row_sumsq(p, D, lane)), 1e-12f);
         else scale = (is_b ? ws->flag_b : ws->flag_a) ? (is_b ? inv_b : inv_a)[row] : 1.0f;
         const size_t off = (size_t)row * Dp;
-        for (int i = lane; i < Dp; i += 32) {
-            const float v = i < D ? __ldg(p + i) * scale : 0.0f;
-            const float h = __int_as_float(__float_as_int(v) & 0xffffe000);     // TF32: 10 explicit mantissa bits
-            const float l = v - h;
+        const bool vec_in = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+        for (int i = 4 * lane; i < Dp; i += 128) {                     // Dp is a multiple of 32: whole float4s
+            float v[4];
+            if (vec_in && i + 4 <= D) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(p + i));
+                v[0] = x.x * scale; v[1] = x.y * scale; v[2] = x.z * scale; v[3] = x.w * scale;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = i + j < D ? __ldg(p + i + j) * scale : 0.0f;
+            }
+            float4 h, l;
+            h.x = __int_as_float(__float_as_int(v[0]) & 0xffffe000);     // TF32: 10 explicit mantissa bits
+            h.y = __int_as_float(__float_as_int(v[1]) & 0xffffe000);
+            h.z = __int_as_float(__float_as_int(v[2]) & 0xffffe000);
+            h.w = __int_as_float(__float_as_int(v[3]) & 0xffffe000);
+            l = make_float4(v[0] - h.x, v[1] - h.y, v[2] - h.z, v[3] - h.w);
             if (!is_b) {
-                dst.a_planes[off + i] = h;
-                dst.a_planes[dst.a_plane_stride + off + i] = l;
+                *reinterpret_cast<float4*>(dst.a_planes + off + i) = h;
+                *reinterpret_cast<float4*>(dst.a_planes + dst.a_plane_stride + off + i) = l;
+            } else if (dst.b_mc) {
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                             ::"l"(dst.b_mc + off + i), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                             ::"l"(dst.b_mc + dst.b_plane_stride + off + i), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
             } else {
 #pragma unroll 1
                 for (int d = 0; d < dst.n_dst; ++d) {
-                    dst.b_dst[d][off + i] = h;
-                    dst.b_dst[d][dst.b_plane_stride + off + i] = l;
+                    *reinterpret_cast<float4*>(dst.b_dst[d] + off + i) = h;
+                    *reinterpret_cast<float4*>(dst.b_dst[d] + dst.b_plane_stride + off + i) = l;
                 }
             }
         }
@@ -540,13 +559,14 @@ int stx_cosine_gather_sizes(int n_local, int m_cap, int world, int D, size_t* ws
     }
     const int Dp = padded_d(D);
     *ws_bytes = 2 * align256(size_t(n_local) * Dp * sizeof(float)) + 256;
-    *symm_bytes = symm_planes_bytes(world, m_cap, Dp) + 256 /* flags */ + 256 /* counter */;
+    // two sets of (planes, flags), used alternately by epoch parity, + the push counter
+    *symm_bytes = 2 * (symm_planes_bytes(world, m_cap, Dp) + 256) + 256;
     return 0;
 }
 
 int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int D, int world, int rank,
-                            const int32_t* h_counts, int m_cap, void* const* h_peer_symm, uint32_t epoch,
-                            float* d_S, void* d_ws, size_t ws_bytes, void* stream) {
+                            const int32_t* h_counts, int m_cap, void* const* h_peer_symm, void* d_multicast,
+                            uint32_t epoch, float* d_S, void* d_ws, size_t ws_bytes, void* stream) {
     using namespace stx;
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_local < 0 || D <= 0 || m_cap <= 0 || !h_counts ||
         !h_peer_symm) {
@@ -566,19 +586,22 @@ int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int Dp = padded_d(D);
     const size_t planes = symm_planes_bytes(world, m_cap, Dp);
+    const size_t set_bytes = planes + 256;                  // planes, then the flags of this set
+    const size_t set_off = size_t(epoch & 1u) * set_bytes;  // calls alternate between two sets: see stx_b200.h
     const size_t slot_floats = size_t(2) * m_cap * Dp;
     float* a_planes = static_cast<float*>(d_ws);
     SplitDst dst = {};
     dst.a_planes = a_planes;  dst.a_plane_stride = size_t(n_local) * Dp;
     dst.b_plane_stride = size_t(m_cap) * Dp;  dst.n_dst = world;
     for (int p = 0; p < world; ++p) {
-        char* base = static_cast<char*>(h_peer_symm[p]);
+        char* base = static_cast<char*>(h_peer_symm[p]) + set_off;
         dst.b_dst[p] = reinterpret_cast<float*>(base) + size_t(rank) * slot_floats;       // my slot in peer p's buffer
         dst.flags[p] = reinterpret_cast<unsigned*>(base + planes);
     }
-    char* mine = static_cast<char*>(h_peer_symm[rank]);
+    if (d_multicast) dst.b_mc = reinterpret_cast<float*>(static_cast<char*>(d_multicast) + set_off) + size_t(rank) * slot_floats;
+    char* mine = static_cast<char*>(h_peer_symm[rank]) + set_off;
     dst.flag_index = rank;  dst.epoch = epoch;
-    dst.counter = reinterpret_cast<unsigned*>(mine + planes + 256);
+    dst.counter = reinterpret_cast<unsigned*>(static_cast<char*>(h_peer_symm[rank]) + 2 * set_bytes);
     // normalise + split + all-gather over NVLink (P2P stores into every peer's slot) in one kernel
     STX_LAUNCH(c_split, dim3((n_local + h_counts[rank] + 7) / 8), dim3(256), 0, st, d_a, d_b, n_local, h_counts[rank], D, Dp,
                nullptr, nullptr, nullptr, dst);
