@@ -160,6 +160,20 @@ int stx_score_pos_neg(const float* d_aud, const float* d_pos, const float* d_neg
                       float* d_hr_pos, float* d_hr_neg, float* d_per_sample, float* d_loss, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The speech encoder's input stage, directly downstream of input_features.
+ * Replaces Wav2Vec2BertFeatureProjection.forward in eval mode (TF/models/wav2vec2_bert/modeling_wav2vec2_bert.py
+ * :118-130, called at :1016): norm = LayerNorm(in_dim, eps)(x); hidden = norm @ weight.T + bias.
+ *   d_x [rows, in_dim] (rows = B * T', in_dim = 160), d_ln_weight / d_ln_bias [in_dim], d_weight [out_dim, in_dim]
+ *   (torch.nn.Linear layout, out_dim = 1024), d_bias [out_dim] or NULL;
+ *   d_hidden [rows, out_dim]; d_norm NULL or [rows, in_dim] (the module's second return value).
+ * The contraction runs on tcgen05 with split-TF32 operands (float32-grade accuracy).
+ * ------------------------------------------------------------------------------------------- */
+int stx_feature_projection_workspace(int rows, int in_dim, int out_dim, size_t* bytes);
+int stx_feature_projection(const float* d_x, const float* d_ln_weight, const float* d_ln_bias, float eps,
+                           const float* d_weight, const float* d_bias, int rows, int in_dim, int out_dim,
+                           float* d_hidden, float* d_norm, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Multi-GPU N x M scoring: this rank's stripe S[rows of a, all M] where the text embeddings b are sharded over
  * `world` ranks of one NVLink/NVSwitch box (BASELINE.json configs[4]).  The reference has no collective; this is the
  * north_star's "all-gathered N x M cosine matrix".  The all-gather is FUSED into the kernels over peer memory:

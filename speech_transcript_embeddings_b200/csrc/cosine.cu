@@ -285,6 +285,51 @@ c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, 
     }
 }
 
+// ---- encoder input stage: LayerNorm(in_dim) + Linear(in_dim -> out_dim) -------------------------
+// Wav2Vec2BertFeatureProjection.forward (TF/models/wav2vec2_bert/modeling_wav2vec2_bert.py:118-130), the first thing
+// the speech encoder does with input_features (:1016).  p_ln_split: one warp per row, torch.nn.LayerNorm semantics
+// (biased variance, eps inside the sqrt), optional copy of the normalised row (the module's second return value), and
+// the TF32 hi / lo planes of it; p_split: planes of the weight matrix; the contraction is c_nxm_tc with a bias epilogue.
+__global__ void __launch_bounds__(256)
+p_ln_split(const float* __restrict__ x, int rows, int D, int Dp, const float* __restrict__ gamma, const float* __restrict__ beta,
+           float eps, float* __restrict__ norm_out, float* __restrict__ planes, size_t plane_stride) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* p = x + (size_t)row * D;
+    float s = 0.0f;
+    for (int i = lane; i < D; i += 32) s += __ldg(p + i);
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.0f;
+    for (int i = lane; i < D; i += 32) { const float d = __ldg(p + i) - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    const size_t off = (size_t)row * Dp;
+    for (int i = lane; i < Dp; i += 32) {
+        float v = 0.0f;
+        if (i < D) {
+            v = (__ldg(p + i) - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i);
+            if (norm_out) norm_out[(size_t)row * D + i] = v;
+        }
+        const float h = __int_as_float(__float_as_int(v) & 0xffffe000);
+        planes[off + i] = h;
+        planes[plane_stride + off + i] = v - h;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+p_split(const float* __restrict__ w, int rows, int D, int Dp, float* __restrict__ planes, size_t plane_stride) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const size_t off = (size_t)row * Dp;
+    for (int i = lane; i < Dp; i += 32) {
+        const float v = i < D ? __ldg(w + (size_t)row * D + i) : 0.0f;
+        const float h = __int_as_float(__float_as_int(v) & 0xffffe000);
+        planes[off + i] = h;
+        planes[plane_stride + off + i] = v - h;
+    }
+}
+
 // Geometry of one launch of c_nxm_tc.  B lives in `world` slots of [hi | lo] planes of b_plane_rows rows each (one slot
 // per source rank; one slot on a single GPU); column tiles are visited in `slot[]` order (own rank first).
 struct TcGeom {
@@ -299,6 +344,7 @@ struct TcGeom {
     int ldS;                        // row pitch of S (total columns)
     const unsigned* flags;          // flags[slot] reaches `epoch` when the slot's planes have landed (nullptr: local data)
     unsigned epoch;
+    const float* bias;              // nullptr, or one value per output column added in the epilogue (feature projection)
 };
 
 __global__ void __launch_bounds__(kTcThreads)
@@ -391,6 +437,11 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                          : "r"(tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (g.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < n_valid) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(g.bias + n0 + c0 + j));
+            }
             if (row < N) {
                 float* dst = S + (size_t)row * M + n0 + c0;
                 if (vec && (n0 & 3) == 0 && c0 + 32 <= n_valid) {
@@ -549,6 +600,41 @@ int stx_score_pos_neg(const float* d_aud, const float* d_pos, const float* d_neg
     STX_LAUNCH(c_pos_neg, dim3((B + 7) / 8), dim3(256), 0, st, d_aud, d_pos, d_neg, B, D, 1.0f / temperature, d_align_factor, o);
     STX_LAUNCH(c_pos_neg_loss, dim3(1), dim3(256), 0, st, d_per_sample, d_s_neg, B, corrupt_gamma, d_loss);
     return 0;
+}
+
+int stx_feature_projection_workspace(int rows, int in_dim, int out_dim, size_t* bytes) {
+    using namespace stx;
+    if (rows < 0 || in_dim <= 0 || out_dim <= 0 || !bytes) { set_error("stx_feature_projection_workspace: bad argument"); return STX_EINVAL; }
+    const size_t Dp = size_t(padded_d(in_dim));
+    *bytes = 2 * align256(size_t(rows) * Dp * sizeof(float)) + 2 * align256(size_t(out_dim) * Dp * sizeof(float));
+    return 0;
+}
+
+int stx_feature_projection(const float* d_x, const float* d_ln_weight, const float* d_ln_bias, float eps, const float* d_weight,
+                           const float* d_bias, int rows, int in_dim, int out_dim, float* d_hidden, float* d_norm,
+                           void* d_ws, size_t ws_bytes, void* stream) {
+    using namespace stx;
+    if (rows < 0 || in_dim <= 0 || out_dim <= 0) { set_error("stx_feature_projection: need rows >= 0, in_dim, out_dim > 0"); return STX_EINVAL; }
+    if (rows == 0) return 0;
+    if (!d_x || !d_ln_weight || !d_ln_bias || !d_weight || !d_hidden || !d_ws) { set_error("stx_feature_projection: null pointer"); return STX_EINVAL; }
+    size_t need = 0;
+    stx_feature_projection_workspace(rows, in_dim, out_dim, &need);
+    if (ws_bytes < need) { set_error("stx_feature_projection: workspace %zu < %zu bytes", ws_bytes, need); return STX_ENOSPACE; }
+    if (int rc = check_device()) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Dp = padded_d(in_dim);
+    float* a_planes = static_cast<float*>(d_ws);
+    float* b_planes = reinterpret_cast<float*>(static_cast<char*>(d_ws) + 2 * align256(size_t(rows) * Dp * sizeof(float)));
+    STX_LAUNCH(p_ln_split, dim3((rows + 7) / 8), dim3(256), 0, st, d_x, rows, in_dim, Dp, d_ln_weight, d_ln_bias, eps, d_norm,
+               a_planes, size_t(rows) * Dp);
+    STX_LAUNCH(p_split, dim3((out_dim + 7) / 8), dim3(256), 0, st, d_weight, out_dim, in_dim, Dp, b_planes, size_t(out_dim) * Dp);
+    TcGeom g = {};
+    g.n_rows = rows;  g.a_plane_rows = rows;  g.b_plane_rows = out_dim;  g.world = 1;
+    g.tiles_start[0] = 0;  g.tiles_start[1] = (out_dim + kTN - 1) / kTN;
+    g.slot[0] = 0;  g.m_count[0] = out_dim;  g.col_start[0] = 0;  g.ldS = out_dim;
+    g.bias = d_bias;
+    if ((rows + kTM - 1) / kTM > 65535) { set_error("stx_feature_projection: more than 65535 row tiles"); return STX_EINVAL; }
+    return launch_gemm(a_planes, 2 * rows, b_planes, 2 * out_dim, Dp, g, g.tiles_start[1], d_hidden, st);
 }
 
 int stx_cosine_gather_sizes(int n_local, int m_cap, int world, int D, size_t* ws_bytes, size_t* symm_bytes) {

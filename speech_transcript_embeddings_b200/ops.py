@@ -235,3 +235,32 @@ def score_pos_neg(aud: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, tempe
                                          out["hr_neg"].data_ptr(), out["per_sample"].data_ptr(), out["loss"].data_ptr(),
                                          _stream_ptr(dev)), "stx_score_pos_neg")
     return out
+
+
+def feature_projection(x: torch.Tensor, ln_weight: torch.Tensor, ln_bias: torch.Tensor, weight: torch.Tensor,
+                       bias: torch.Tensor | None = None, eps: float = 1e-5, return_norm: bool = True):
+    """``Wav2Vec2BertFeatureProjection.forward`` in eval mode (TF/models/wav2vec2_bert/modeling_wav2vec2_bert.py:118-130):
+    x [..., in_dim] -> (hidden [..., out_dim], norm [..., in_dim] or None); the Linear runs on tcgen05."""
+    lib = _lib.load()
+    _require_cuda(x, "x", torch.float32)
+    for name, t in (("ln_weight", ln_weight), ("ln_bias", ln_bias), ("weight", weight)):
+        _require_cuda(t, name, torch.float32)
+    if bias is not None:
+        _require_cuda(bias, "bias", torch.float32)
+    in_dim = x.shape[-1]
+    out_dim = weight.shape[0]
+    if weight.shape != (out_dim, in_dim) or ln_weight.shape != (in_dim,) or ln_bias.shape != (in_dim,):
+        raise ValueError("shape mismatch between x, the LayerNorm parameters and the Linear weight")
+    rows = x.numel() // in_dim
+    dev = x.device
+    hidden = torch.empty(x.shape[:-1] + (out_dim,), dtype=torch.float32, device=dev)
+    norm = torch.empty_like(x) if return_norm else None
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_feature_projection_workspace(rows, in_dim, out_dim, C.byref(nbytes)), "stx_feature_projection_workspace")
+    ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_feature_projection(x.data_ptr(), ln_weight.data_ptr(), ln_bias.data_ptr(), float(eps),
+                                              weight.data_ptr(), bias.data_ptr() if bias is not None else None, rows, in_dim,
+                                              out_dim, hidden.data_ptr(), norm.data_ptr() if norm is not None else None,
+                                              ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "stx_feature_projection")
+    return hidden, norm
