@@ -102,6 +102,21 @@ __device__ __forceinline__ StageRange stage_range(int g0, int len, bool aligned)
     return r;
 }
 
+// log10(x) for normal positive x (the 1e-10 floor guarantees it): exponent + MUFU.LG2 of the mantissa, times log10(2).
+// The mantissa's log2 is in [0, 1), where lg2.approx is accurate to 2^-22 absolute, so the result is within 1e-7 of
+// log10f at a third of its instructions (the bar on log10 is 4e-4).
+__device__ __forceinline__ float log10_pos(float x) {
+    const int bits = __float_as_int(x);
+    const float e = (float)((bits >> 23) - 127);
+    const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+    float l2;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(l2) : "f"(m));
+    constexpr float k_hi = 0.30102539062500f;             // log10(2) to 12 significant bits: e * k_hi is exact
+    constexpr float k_lo = 4.6050389811952137e-6f;        // log10(2) - k_hi
+    constexpr float k = 0.30102999566398120f;
+    return fmaf(e, k_hi, fmaf(l2, k, e * k_lo));
+}
+
 template <int kSlot>
 __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const float* __restrict__ melw,
                                           const int* __restrict__ melfirst, int warp) {
@@ -117,7 +132,7 @@ __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const fl
         acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
         acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
     }
-    return log10f(fmaxf(acc0 + acc1, 1e-10f));
+    return log10_pos(fmaxf(acc0 + acc1, 1e-10f));
 }
 
 // Per-clip max through an order-preserving integer key (negative floats: all bits flipped, others: sign bit set), so
@@ -174,7 +189,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         if (g0 >= len && len <= n_samples - (kN / 2 + 2)) {
             // the whole tile lies in the zero padding behind the clip (and the reflected tail of the padded signal is
             // zero as well): every mel energy is 0, so every value is log10 of the floor; no copy was issued for it
-            const float v = log10f(1e-10f);
+            const float v = log10_pos(1e-10f);
             const int t = t0 + lane;
             if (t < t_end) {
 #pragma unroll
@@ -185,13 +200,13 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         }
         const StageRange sr = stage_range(g0, len, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
-        if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {
+        if (sr.lo == g0 && sr.hi == g0 + kTileSamples && peak == 1.0f) {
 #pragma unroll 1
-            for (int i = tid; i < kTileSamples; i += kThreads) {
-                float x = sm.stage[i];
-                if (peak != 1.0f) x = x / peak;                // float32 division, like numpy's (R/processor.py:92)
-                sm.xs[i + (unsigned)i / kHop] = x;
-            }
+            for (int i = tid; i < kTileSamples; i += kThreads) sm.xs[i + (unsigned)i / kHop] = sm.stage[i];
+        } else if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {
+#pragma unroll 1
+            for (int i = tid; i < kTileSamples; i += kThreads)
+                sm.xs[i + (unsigned)i / kHop] = sm.stage[i] / peak;    // float32 division, like numpy's (R/processor.py:92)
         } else {
 #pragma unroll 1
             for (int i = tid; i < kTileSamples; i += kThreads) {
