@@ -11,6 +11,7 @@
 //   c_split + c_nxm_tc   the N x M matrix on tcgen05 tensor cores with split-TF32 operands (see below)
 #include "stx_common.h"
 #include <cuda.h>
+#include <algorithm>
 
 namespace stx {
 namespace {
@@ -146,22 +147,28 @@ c_pos_neg_loss(const float* __restrict__ per_sample, const float* __restrict__ s
 //
 //   c_split    one warp per row: scale by 1/||x|| (or 1), write hi and lo planes with rows zero-padded to a
 //              multiple of 32 floats (one 128-byte swizzle row per k-block)
-//   c_nxm_tc   128 x 128 tile per CTA, 192 threads: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B,
+//   c_nxm_tc   persistent: one CTA per SM walks 128 x 128 output tiles (column-major, so CTAs running together
+//              share the B tile in L2).  192 threads: warp 0 = TMA producer (cp.async.bulk.tensor, SWIZZLE_128B boxes
+//              of 128 rows x 128 B; per k-block the hi AND lo planes of both operands land once, 64 KB per stage,
 //              3-stage full/empty mbarrier ring), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer
-//              (kind::tf32, M = 128, N = 128, K = 8; tcgen05.commit frees the stage), warps 2-5 = epilogue
-//              (tcgen05.ld 32x32b.x32 -> registers -> 128-byte row segments of S)
+//              (kind::tf32, M = 128, N = 128, K = 8: per k-block hi.hi, lo.hi and hi.lo from the same stage;
+//              tcgen05.commit frees the stage), warps 2-5 = epilogue (tcgen05.ld 32x32b.x32 -> registers -> 128-byte
+//              row segments of S).  Two accumulators in TMEM (2 x 128 columns): the epilogue of tile i overlaps the
+//              main loop of tile i + 1.
 constexpr int kTM = 128, kTN = 128, kTK = 32, kStages = 3;
 constexpr int kTcThreads = 192;
-constexpr int kTileABytes = kTM * kTK * 4, kTileBBytes = kTN * kTK * 4;
-constexpr unsigned kTmemCols = 128;
+constexpr int kTileBytes = kTM * kTK * 4;       // one 128 x 32 float plane tile
+constexpr unsigned kTmemCols = 256;             // two 128 x 128 float accumulators
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major A and B,
 // N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr unsigned kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTN >> 3) << 17) | ((unsigned)(kTM >> 4) << 24);
 
 struct TcSmem {
-    unsigned char a[kStages][kTileABytes];      // [128 rows][128 B], 128-byte swizzle, 1024-byte aligned
-    unsigned char b[kStages][kTileBBytes];
-    unsigned long long full[kStages], empty[kStages], tmem_full;
+    unsigned char a_hi[kStages][kTileBytes];    // [128 rows][128 B], 128-byte swizzle, 1024-byte aligned
+    unsigned char a_lo[kStages][kTileBytes];
+    unsigned char b_hi[kStages][kTileBytes];
+    unsigned char b_lo[kStages][kTileBytes];
+    unsigned long long full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
     unsigned tmem_base;
 };
 
@@ -347,28 +354,37 @@ struct TcGeom {
     const float* bias;              // nullptr, or one value per output column added in the epilogue (feature projection)
 };
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 1)
 c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-         const __grid_constant__ TcGeom g, int kb_per_pass, float* __restrict__ S) {
+         const __grid_constant__ TcGeom g, int kb_per_pass, int n_col_tiles, float* __restrict__ S) {
     extern __shared__ unsigned char smem_raw[];
     TcSmem& sm = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kTM;
-    int ord = 0;
-    while (ord + 1 < g.world && (int)blockIdx.x >= g.tiles_start[ord + 1]) ++ord;
-    const int slot = g.slot[ord];
-    const int j0 = ((int)blockIdx.x - g.tiles_start[ord]) * kTN;          // first row of the tile inside its slot
-    const int n0 = g.col_start[slot] + j0;                                // first output column
-    const int n_valid = min(kTN, g.m_count[slot] - j0);
-    const int b_row_hi = (slot * 2) * g.b_plane_rows + j0, b_row_lo = b_row_hi + g.b_plane_rows;
     const int N = g.n_rows, M = g.ldS;
-    const int num_kb = 3 * kb_per_pass;
+    const int n_row_tiles = (N + kTM - 1) / kTM;
+    const int num_tiles = n_row_tiles * n_col_tiles;
+
+    // tile t -> (row tile, column tile, slot geometry); column-major: tiles that run together share their B tile
+    struct Tile { int m0, slot, j0, n0, n_valid, b_row_hi; };
+    auto tile_of = [&](int t) {
+        Tile ti;
+        const int ct = t / n_row_tiles;
+        ti.m0 = (t - ct * n_row_tiles) * kTM;
+        int ord = 0;
+        while (ord + 1 < g.world && ct >= g.tiles_start[ord + 1]) ++ord;
+        ti.slot = g.slot[ord];
+        ti.j0 = (ct - g.tiles_start[ord]) * kTN;                        // first row of the tile inside its slot
+        ti.n0 = g.col_start[ti.slot] + ti.j0;                           // first output column
+        ti.n_valid = min(kTN, g.m_count[ti.slot] - ti.j0);
+        ti.b_row_hi = (ti.slot * 2) * g.b_plane_rows + ti.j0;
+        return ti;
+    };
 
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-            mbar_init(&sm.tmem_full, 1);
+            for (int a = 0; a < 2; ++a) { mbar_init(&sm.tmem_full[a], 1); mbar_init(&sm.tmem_empty[a], 4); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -383,81 +399,108 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            if (g.flags) {
-                // the slot's planes are written by its source rank over NVLink: acquire its flag, then order the
-                // generic-proxy view before the async-proxy (TMA) reads
-                unsigned v;
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g.flags + slot) : "memory");
-                    if ((int)(v - g.epoch) < 0) __nanosleep(64);
-                } while ((int)(v - g.epoch) < 0);
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages, it = kb / kStages;
-                if (it > 0) mbar_wait(&sm.empty[s], (unsigned)(it - 1) & 1u);
-                const int pass = kb / kb_per_pass, k0 = (kb - pass * kb_per_pass) * kTK;
-                mbar_expect_tx(&sm.full[s], kTileABytes + kTileBBytes);
-                tma_load_2d(sm.a[s], &map_a, k0, pass == 1 ? m0 + g.a_plane_rows : m0, &sm.full[s]);
-                tma_load_2d(sm.b[s], &map_b, k0, pass == 2 ? b_row_lo : b_row_hi, &sm.full[s]);
+            int it = 0;                              // k-blocks issued so far, over all of this CTA's tiles
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const Tile ti = tile_of(t);
+                if (g.flags) {
+                    // the slot's planes are written by its source rank over NVLink: acquire its flag, then order the
+                    // generic-proxy view before the async-proxy (TMA) reads
+                    unsigned v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(g.flags + ti.slot) : "memory");
+                        if ((int)(v - g.epoch) < 0) __nanosleep(64);
+                    } while ((int)(v - g.epoch) < 0);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                for (int kb = 0; kb < kb_per_pass; ++kb, ++it) {
+                    const int s = it % kStages, round = it / kStages;
+                    if (round > 0) mbar_wait(&sm.empty[s], (unsigned)(round - 1) & 1u);
+                    mbar_expect_tx(&sm.full[s], 4 * kTileBytes);
+                    tma_load_2d(sm.a_hi[s], &map_a, kb * kTK, ti.m0, &sm.full[s]);
+                    tma_load_2d(sm.a_lo[s], &map_a, kb * kTK, ti.m0 + g.a_plane_rows, &sm.full[s]);
+                    tma_load_2d(sm.b_hi[s], &map_b, kb * kTK, ti.b_row_hi, &sm.full[s]);
+                    tma_load_2d(sm.b_lo[s], &map_b, kb * kTK, ti.b_row_hi + g.b_plane_rows, &sm.full[s]);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages, it = kb / kStages;
-                mbar_wait(&sm.full[s], (unsigned)it & 1u);
+            int it = 0, n = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++n) {
+                const int acc = n & 1;
+                if (n >= 2) mbar_wait(&sm.tmem_empty[acc], (unsigned)(n / 2 - 1) & 1u);     // the epilogue has drained it
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned d = tmem + (unsigned)(acc * kTN);
+                for (int kb = 0; kb < kb_per_pass; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&sm.full[s], (unsigned)(it / kStages) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < kTK / 8; ++k)
-                    umma_tf32(tmem, umma_desc(sm.a[s], k * 32), umma_desc(sm.b[s], k * 32), (kb | k) != 0);
-                umma_commit(&sm.empty[s]);          // the stage is free once these MMAs have read it
+                    for (int k = 0; k < kTK / 8; ++k) {
+                        const unsigned long long ah = umma_desc(sm.a_hi[s], k * 32), al = umma_desc(sm.a_lo[s], k * 32);
+                        const unsigned long long bh = umma_desc(sm.b_hi[s], k * 32), bl = umma_desc(sm.b_lo[s], k * 32);
+                        umma_tf32(d, ah, bh, (kb | k) != 0);
+                        umma_tf32(d, al, bh, 1);
+                        umma_tf32(d, ah, bl, 1);
+                    }
+                    umma_commit(&sm.empty[s]);      // the stage is free once these MMAs have read it
+                }
+                umma_commit(&sm.tmem_full[acc]);    // accumulator complete
             }
-            umma_commit(&sm.tmem_full);             // accumulator complete
         }
         __syncwarp();
     } else {
         // ===== epilogue: TMEM -> registers -> global =====
-        mbar_wait(&sm.tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                     // a warp can only read its own quarter of the TMEM lanes
-        const int row = m0 + q * 32 + lane;
         const bool vec = (M & 3) == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0;
+        int n = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++n) {
+            const Tile ti = tile_of(t);
+            const int acc = n & 1;
+            mbar_wait(&sm.tmem_full[acc], (unsigned)(n / 2) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = ti.m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kTN; c0 += 32) {
-            unsigned r[32];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                         : "r"(tmem + ((unsigned)(q * 32) << 16) + (unsigned)c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (g.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < n_valid) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(g.bias + n0 + c0 + j));
-            }
-            if (row < N) {
-                float* dst = S + (size_t)row * M + n0 + c0;
-                if (vec && (n0 & 3) == 0 && c0 + 32 <= n_valid) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                } else {
+            for (int c0 = 0; c0 < kTN; c0 += 32) {
+                unsigned r[32];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(acc * kTN + c0)));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 >= ti.n_valid) continue;
+                if (g.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < n_valid) dst[j] = __uint_as_float(r[j]);
+                        if (c0 + j < ti.n_valid) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(g.bias + ti.n0 + c0 + j));
+                }
+                if (row < N) {
+                    float* dst = S + (size_t)row * M + ti.n0 + c0;
+                    if (vec && (ti.n0 & 3) == 0 && c0 + 32 <= ti.n_valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < ti.n_valid) dst[j] = __uint_as_float(r[j]);
+                    }
                 }
             }
+            // this warp is done with the accumulator: one arrival per epilogue warp frees it for tile n + 2
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sm.tmem_empty[acc])) : "memory");
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -505,8 +548,11 @@ int launch_gemm(const float* a_planes, int a_rows_total, const float* b_planes, 
         STX_CUDA(cudaFuncSetAttribute(c_nxm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set[dev] = true;
     }
-    STX_LAUNCH(c_nxm_tc, dim3(n_col_tiles, (g.n_rows + kTM - 1) / kTM), dim3(kTcThreads), smem_bytes, st,
-               ma, mb, g, Dp / kTK, d_S);
+    static int sms[64] = {0};
+    if (dev >= 0 && dev < 64 && !sms[dev]) STX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    const long long tiles = (long long)n_col_tiles * ((g.n_rows + kTM - 1) / kTM);
+    const int ctas = (int)std::min<long long>(tiles, (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148);
+    STX_LAUNCH(c_nxm_tc, dim3(ctas), dim3(kTcThreads), smem_bytes, st, ma, mb, g, Dp / kTK, n_col_tiles, d_S);
     return 0;
 }
 
@@ -633,7 +679,6 @@ int stx_feature_projection(const float* d_x, const float* d_ln_weight, const flo
     g.tiles_start[0] = 0;  g.tiles_start[1] = (out_dim + kTN - 1) / kTN;
     g.slot[0] = 0;  g.m_count[0] = out_dim;  g.col_start[0] = 0;  g.ldS = out_dim;
     g.bias = d_bias;
-    if ((rows + kTM - 1) / kTM > 65535) { set_error("stx_feature_projection: more than 65535 row tiles"); return STX_EINVAL; }
     return launch_gemm(a_planes, 2 * rows, b_planes, 2 * out_dim, Dp, g, g.tiles_start[1], d_hidden, st);
 }
 
