@@ -11,12 +11,12 @@
 // FFT therefore run on the FP64 pipe; everything after the power spectrum is float32 like the
 // reference's own rounding points (complex64 spectrum, float32 log-mel).
 //
-// Three kernels:
+// Two kernels:
 //   k_frames    one CTA per (clip, chunk of frames): PCM -> raw log-mel (written in place into the
 //               output tensor, whose [T_pad/2,160] rows are exactly [T_pad,80] rows) + per-chunk
 //               per-bin (sum, sum of squares) partials in fixed point (int64)
-//   k_finalize  one CTA per clip: integer sum of the partials -> mean, 1/sqrt(var_ddof1 + 1e-7)
-//   k_normalize in-place CMVN, padding rows, attention mask (the extractor's int32 mask, or the trainer
+//   k_normalize every CTA sums its clip's partials (integers: same result in every CTA) -> mean,
+//               1/sqrt(var_ddof1 + 1e-7); then in-place CMVN, padding rows, attention mask (the extractor's int32 mask, or the trainer
 //               collate's int64 mask with zero rows past the clip: R/training/trainer_unfreeze.py:898-908)
 //
 // k_frames keeps ONE FRAME PER LANE: a tile is 32 consecutive frames of a clip and the 16 warps of the
@@ -421,31 +421,6 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     }
 }
 
-// mean and 1/sqrt(var + 1e-7) per (clip, bin); var with ddof = 1 (…seamless_m4t.py:257-262)
-__global__ void k_finalize(const int* __restrict__ lengths, const long long* __restrict__ partials, int chunk_frames,
-                           int chunks_per_clip, double* __restrict__ stats) {
-    const int b = blockIdx.x, m = threadIdx.x;
-    if (m >= kMel) return;
-    const int n = lengths[b];
-    const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
-    const int nchunks = (T + chunk_frames - 1) / chunk_frames;
-    long long i1 = 0, i2h = 0, i2l = 0;                            // exact: integer sums are order-independent
-    for (int c = 0; c < nchunks; ++c) {
-        const long long* p = partials + ((size_t)b * chunks_per_clip + c) * kStatWords;
-        i1 += p[m];
-        i2h += p[kMel + m];
-        i2l += p[2 * kMel + m];
-    }
-    const double a1 = (double)i1 * (1.0 / 4294967296.0);
-    const double a2 = (double)i2h * (1.0 / 1048576.0) + (double)i2l * (1.0 / 72057594037927936.0);
-    const double mean = a1 / (double)T;
-    // a single frame has no ddof=1 variance: numpy returns NaN there and so do we
-    double var = T > 1 ? (a2 - a1 * mean) / (double)(T - 1) : __longlong_as_double(0x7ff8000000000000LL);
-    if (var < 0.0) var = 0.0;                                      // rounding of a constant column; keeps NaN
-    stats[((size_t)b * kMel + m) * 2 + 0] = mean;
-    stats[((size_t)b * kMel + m) * 2 + 1] = 1.0 / sqrt(var + 1e-7);
-}
-
 // in-place CMVN + padding rows + mask.  One thread per float4 of a clip's [T_pad, 80] block.
 //   rows t < T            normalised features
 //   rows T <= t < T2      padding_value (T2 = T rounded up to even: the half of the last stacked frame of an odd clip)
@@ -454,16 +429,38 @@ __global__ void k_finalize(const int* __restrict__ lengths, const long long* __r
 //   mask_mode 0: int32, mask[j] = (2 j + 1 < T)  (…seamless_m4t.py:292-293);  1: int64, mask[j] = (2 j < T), i.e. every
 //   stacked frame the per-clip extractor call returned (R/training/trainer_unfreeze.py:904-908)
 __global__ void __launch_bounds__(256)
-k_normalize(const int* __restrict__ lengths, const double* __restrict__ stats, int T_pad, float padding_value,
-            float tail_value, int normalize, float* __restrict__ out, void* __restrict__ mask, int mask_mode) {
+k_normalize(const int* __restrict__ lengths, const long long* __restrict__ partials, int chunk_frames, int chunks_per_clip,
+            int T_pad, float padding_value, float tail_value, int normalize, float* __restrict__ out,
+            void* __restrict__ mask, int mask_mode) {
     __shared__ double s_mean[kMel], s_rstd[kMel];
+    __shared__ long long s_sum[kStatWords];
     const int b = blockIdx.y;
     const int n = lengths[b];
-    const int T = min(n >= kFrame ? 1 + (n - kFrame) / kHop : 0, T_pad);
+    const int T_all = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;      // the statistics are over ALL frames of the clip
+    const int T = min(T_all, T_pad);
     const int T2 = min((T + 1) & ~1, T_pad);
-    if (threadIdx.x < kMel) {
-        s_mean[threadIdx.x] = stats[((size_t)b * kMel + threadIdx.x) * 2 + 0];
-        s_rstd[threadIdx.x] = stats[((size_t)b * kMel + threadIdx.x) * 2 + 1];
+    // mean and 1/sqrt(var + 1e-7) per bin, var with ddof = 1 (…seamless_m4t.py:257-262): integer sums of the chunk
+    // partials are exact and order-independent, so every CTA of the clip (and every batch) gets the same bits
+    if (normalize && T_all > 0) {
+        const int nchunks = (T_all + chunk_frames - 1) / chunk_frames;
+        if (threadIdx.x < kStatWords) {
+            long long acc = 0;
+            const long long* p = partials + (size_t)b * chunks_per_clip * kStatWords + threadIdx.x;
+            for (int c = 0; c < nchunks; ++c) acc += __ldg(p + (size_t)c * kStatWords);
+            s_sum[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < kMel) {
+            const int m = threadIdx.x;
+            const double a1 = (double)s_sum[m] * (1.0 / 4294967296.0);
+            const double a2 = (double)s_sum[kMel + m] * (1.0 / 1048576.0) + (double)s_sum[2 * kMel + m] * (1.0 / 72057594037927936.0);
+            const double mean = a1 / (double)T_all;
+            // a single frame has no ddof=1 variance: numpy returns NaN there and so do we
+            double var = T_all > 1 ? (a2 - a1 * mean) / (double)(T_all - 1) : __longlong_as_double(0x7ff8000000000000LL);
+            if (var < 0.0) var = 0.0;                                  // rounding of a constant column; keeps NaN
+            s_mean[m] = mean;
+            s_rstd[m] = 1.0 / sqrt(var + 1e-7);
+        }
     }
     __syncthreads();
     const int quads = T_pad * (kMel / 4);
@@ -601,8 +598,7 @@ int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     using namespace stx;
     if (B < 0 || max_length < 0 || !bytes) { set_error("stx_fbank_k_workspace: bad argument"); return STX_EINVAL; }
     const int chunks = (frames_of(max_length) + kMinChunk - 1) / kMinChunk;
-    *bytes = align256(size_t(B) * std::max(chunks, 1) * kStatWords * sizeof(long long)) +
-             align256(size_t(B) * kMel * 2 * sizeof(double));
+    *bytes = align256(size_t(B) * std::max(chunks, 1) * kStatWords * sizeof(long long));
     return 0;
 }
 
@@ -623,7 +619,6 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
     const int max_frames = frames_of(max_length);
-    const int ws_chunks = std::max((max_frames + kMinChunk - 1) / kMinChunk, 1);
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -633,8 +628,6 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
     const int chunk_frames = pick_chunk(B, max_frames, sms);
     const int chunks = std::max((max_frames + chunk_frames - 1) / chunk_frames, 1);
     long long* partials = static_cast<long long*>(d_ws);
-    double* stats = reinterpret_cast<double*>(static_cast<char*>(d_ws) +
-                                              align256(size_t(B) * ws_chunks * kStatWords * sizeof(long long)));
     if (frames_of(max_length) > 0) {
         if (d_peak) {
             STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
@@ -646,11 +639,10 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
                        chunk_frames, chunks, d_out, partials);
         }
     }
-    STX_LAUNCH(k_finalize, dim3(B), dim3(96), 0, st, d_lengths, partials, chunk_frames, chunks, stats);
     const int quads = T_pad * (kMel / 4);
     const int gx = std::max(1, std::min((quads + 255) / 256, 64));
-    STX_LAUNCH(k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, stats, T_pad, padding_value, tail_value, normalize,
-               d_out, d_mask, mask_mode);
+    STX_LAUNCH(k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, partials, chunk_frames, chunks, T_pad, padding_value,
+               tail_value, normalize, d_out, d_mask, mask_mode);
     return 0;
 }
 
