@@ -250,12 +250,21 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             return v;
         };
         if (sr.lo == s0 - kLead && sr.hi == s0 + kTileSamples + 4) {
-            // whole tile staged and inside the clip: no range checks
-#pragma unroll 1
-            for (int i = tid; i < kTileSamples; i += kThreads) {
-                float xm = sm.stage[kLead - 1 + i], xi = sm.stage[kLead + i];
-                if (kPeak) { xm = xm / peak; xi = xi / peak; }
-                sm.u.d[i + (unsigned)i / kHop] = fma(-0.97, (double)xm, (double)xi);
+            // whole tile staged and inside the clip: no range checks.  480 threads, thread (r0, c0) = (tid / 160, tid % 160)
+            // converts samples 160 (r0 + 3 j) + c0: no division in the loop, and the iterations are independent
+            // (unrolled: the LDS -> F2F -> DFMA -> STS chains of several samples overlap)
+            if (tid < 3 * kHop) {
+                const int r0 = tid / kHop, c0 = tid - r0 * kHop;
+                const float* src = sm.stage + kLead + r0 * kHop + c0;
+                double* dst = sm.u.d + r0 * kDRow + c0;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    if (j < 11 || r0 * kHop + c0 < kTileSamples - 33 * kHop) {      // rows 0..32 are whole, row 33 holds 80 samples
+                        float xm = src[3 * kHop * j - 1], xi = src[3 * kHop * j];
+                        if (kPeak) { xm = xm / peak; xi = xi / peak; }
+                        dst[3 * kDRow * j] = fma(-0.97, (double)xm, (double)xi);
+                    }
+                }
             }
             if (tid < kTile) {
                 float xa = sm.stage[kLead + tid * kHop + kFrame - 1], xz = sm.stage[kLead - 1 + tid * kHop];

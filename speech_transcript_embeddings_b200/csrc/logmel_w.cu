@@ -201,8 +201,16 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         const StageRange sr = stage_range(g0, len, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         if (sr.lo == g0 && sr.hi == g0 + kTileSamples && peak == 1.0f) {
-#pragma unroll 1
-            for (int i = tid; i < kTileSamples; i += kThreads) sm.xs[i + (unsigned)i / kHop] = sm.stage[i];
+            // 480 threads, thread (r0, c0) = (tid / 160, tid % 160) moves samples 160 (r0 + 3 j) + c0: no division, and
+            // the twelve copies are independent (unrolled)
+            if (tid < 3 * kHop) {
+                const int r0 = tid / kHop, c0 = tid - r0 * kHop;
+                const float* src = sm.stage + r0 * kHop + c0;
+                float* dst = sm.xs + r0 * kXRow + c0;
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    if (j < 11 || r0 * kHop + c0 < kTileSamples - 33 * kHop) dst[3 * kXRow * j] = src[3 * kHop * j];
+            }
         } else if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {
 #pragma unroll 1
             for (int i = tid; i < kTileSamples; i += kThreads)
