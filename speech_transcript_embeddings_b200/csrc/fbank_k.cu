@@ -455,7 +455,15 @@ k_normalize(const int* __restrict__ lengths, const long long* __restrict__ parti
         if (threadIdx.x < kStatWords) {
             long long acc = 0;
             const long long* p = partials + (size_t)b * chunks_per_clip * kStatWords + threadIdx.x;
-            for (int c = 0; c < nchunks; ++c) acc += __ldg(p + (size_t)c * kStatWords);
+            int c = 0;
+            for (; c + 8 <= nchunks; c += 8) {                            // 8 independent L2 loads in flight
+                long long v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(c + u) * kStatWords);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += v[u];
+            }
+            for (; c < nchunks; ++c) acc += __ldg(p + (size_t)c * kStatWords);
             s_sum[threadIdx.x] = acc;
         }
         __syncthreads();
