@@ -9,8 +9,9 @@
 // The reference's default path is float32 (torch.stft); this kernel is float32 throughout.
 //
 //   w_frames    one CTA per (clip, chunk of frames), ONE FRAME PER LANE like k_frames (fbank_k.cu): a tile is 32
-//               consecutive frames and the 16 warps split each frame's 400-point real FFT
-//               (n = 16 n1 + n2, k = k1 + 25 k2):
+//               consecutive frames and the 8 warps split each frame's 400-point real FFT into 16 roles, two per
+//               warp in sequence (n = 16 n1 + n2, k = k1 + 25 k2).  In float32 the exchange is 50 KB per tile, so
+//               two CTAs fit on an SM and overlap each other's phases:
 //                 stage    cp.async.bulk (TMA) of the tile's raw samples, one tile ahead
 //                 layout   reflect / zero padding and the peak divisor applied once per sample, rows of 161 floats
 //                 pass 1   warp n2: Hann window, real DFT-25 over n1 in registers (codelets.cuh), times W400^(n2 k1)
@@ -38,8 +39,9 @@ constexpr int kHop = STX_W_HOP;         // 160
 constexpr int kMel = STX_W_NMEL;        // 80
 constexpr int kBins = kN / 2 + 1;       // 201
 constexpr int kTile = 32;               // frames per tile = lanes
-constexpr int kWarps = 16;
-constexpr int kThreads = kWarps * 32;   // 512
+constexpr int kWarps = 8;                // every warp takes two of the 16 roles, one after the other
+constexpr int kThreads = kWarps * 32;   // 256 threads, ~99 KB of shared memory: two CTAs per SM, so that one CTA's
+                                        // shared-memory phases overlap the other's arithmetic
 constexpr int kTileSamples = (kTile - 1) * kHop + kN;   // 5360
 constexpr int kXRow = kHop + 1;         // padded rows: odd stride, lane f reads row f + const without bank conflicts
 constexpr int kXBuf = 34 * kXRow;
@@ -58,15 +60,17 @@ struct WTables {
 struct Smem {
     float2 ex[12][16][kTile];           // pass-1 rows k1 = 1..12: [k1 - 1][n2][lane]
     float  ex0[16][kTile];              // row k1 = 0 (real)
-    float  P[kBins][kTile];             // power spectrum [bin][lane]
-    float  xs[kXBuf + 2];               // padded, windowable samples of the tile (+2: keeps `stage` 16-byte aligned)
+    union {
+        float xs[kXBuf + 2];            // padded, windowable samples of the tile (dead after pass 1)
+        float P[kBins][kTile];          // power spectrum [bin][lane] (pass 2 -> mel)
+    } u;
     float  stage[kTileSamples];         // raw PCM of the next tile (cp.async.bulk)
     float  melw[kMelWeights];
     int    melfirst[kMel];
     float  wmax[kWarps];
     unsigned long long mbar;
 };
-static_assert(sizeof(Smem) <= 227 * 1024, "shared memory");
+static_assert(sizeof(Smem) + 1024 <= 233472 / 2, "two CTAs per SM: 2 x (dynamic + 1 KB reserved) <= 228 KB");
 static_assert(offsetof(Smem, stage) % 16 == 0, "bulk-copy destination alignment");
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -148,7 +152,7 @@ __device__ __forceinline__ float max_unkey(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
          const float* __restrict__ peaks, const WTables* __restrict__ tab, int n_samples, int chunk_frames,
          float* __restrict__ out, unsigned* __restrict__ clip_max) {
@@ -196,7 +200,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             const int t = t0 + lane;
             if (t < t_end) {
 #pragma unroll
-                for (int i = 0; i < 5; ++i) out_b[(size_t)(warp + 16 * i) * T + t] = v;
+                for (int i = 0; i < 10; ++i) out_b[(size_t)(warp + 8 * i) * T + t] = v;
                 run_max = fmaxf(run_max, v);
             }
             continue;
@@ -204,20 +208,18 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         const StageRange sr = stage_range(g0, len, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         if (sr.lo == g0 && sr.hi == g0 + kTileSamples && peak == 1.0f) {
-            // 480 threads, thread (r0, c0) = (tid / 160, tid % 160) moves samples 160 (r0 + 3 j) + c0: no division, and
-            // the twelve copies are independent (unrolled)
-            if (tid < 3 * kHop) {
-                const int r0 = tid / kHop, c0 = tid - r0 * kHop;
-                const float* src = sm.stage + r0 * kHop + c0;
-                float* dst = sm.xs + r0 * kXRow + c0;
-#pragma unroll
-                for (int j = 0; j < 12; ++j)
-                    if (j < 11 || r0 * kHop + c0 < kTileSamples - 33 * kHop) dst[3 * kXRow * j] = src[3 * kHop * j];
+            // 160 threads, one column each, row by row: no division, independent copies (unrolled)
+            if (tid < kHop) {
+                const float* src = sm.stage + tid;
+                float* dst = sm.u.xs + tid;
+#pragma unroll 11
+                for (int r = 0; r < 33; ++r) dst[kXRow * r] = src[kHop * r];
+                if (tid < kTileSamples - 33 * kHop) dst[kXRow * 33] = src[kHop * 33];
             }
         } else if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {
 #pragma unroll 1
             for (int i = tid; i < kTileSamples; i += kThreads)
-                sm.xs[i + (unsigned)i / kHop] = sm.stage[i] / peak;    // float32 division, like numpy's (R/processor.py:92)
+                sm.u.xs[i + (unsigned)i / kHop] = sm.stage[i] / peak;    // float32 division, like numpy's (R/processor.py:92)
         } else {
 #pragma unroll 1
             for (int i = tid; i < kTileSamples; i += kThreads) {
@@ -228,10 +230,10 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 if (g >= sr.lo && g < sr.hi) x = sm.stage[g - g0];
                 else if (g >= 0 && g < len) x = __ldg(clip + g);
                 if (peak != 1.0f) x = x / peak;
-                sm.xs[i + (unsigned)i / kHop] = x;
+                sm.u.xs[i + (unsigned)i / kHop] = x;
             }
         }
-        __syncthreads();                            // xs ready; staging is free; the previous tile's mel stage is done with P
+        __syncthreads();                            // xs ready; staging is free
 
         if (tid == 0 && t0 + kTile < t_end) {
             const StageRange nx = stage_range(g0 + kTile * kHop, len, aligned);
@@ -241,64 +243,70 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             }
         }
 
-        // ---- window + pass 1 (warp = n2) ----
-        {
-            const float* X = sm.xs + kXRow * lane + warp;
+        // ---- window + pass 1 (role = n2 = warp, warp + 8) ----
+#pragma unroll 1
+        for (int role = warp; role < 16; role += kWarps) {
+            const float* X = sm.u.xs + kXRow * lane + role;
             float y[25], re[13], im[13];
 #pragma unroll
-            for (int n1 = 0; n1 < 25; ++n1) y[n1] = cw_win[warp][n1] * X[16 * n1 + (n1 >= 10) + (n1 >= 20)];
+            for (int n1 = 0; n1 < 25; ++n1) y[n1] = cw_win[role][n1] * X[16 * n1 + (n1 >= 10) + (n1 >= 20)];
             codelets::w_pass1<float>(y, re, im);
-            sm.ex0[warp][lane] = re[0];
+            sm.ex0[role][lane] = re[0];
 #pragma unroll
             for (int k1 = 1; k1 < 13; ++k1) {
-                const float2 t = cw_tw[warp][k1];
-                sm.ex[k1 - 1][warp][lane] = make_float2(fmaf(re[k1], t.x, -(im[k1] * t.y)), fmaf(re[k1], t.y, im[k1] * t.x));
+                const float2 t = cw_tw[role][k1];
+                sm.ex[k1 - 1][role][lane] = make_float2(fmaf(re[k1], t.x, -(im[k1] * t.y)), fmaf(re[k1], t.y, im[k1] * t.x));
             }
         }
-        __syncthreads();
+        __syncthreads();                            // exchange complete; xs is dead, its storage becomes the power spectrum
 
-        // ---- pass 2 (warp = k1 <= 12) + power ----
-        if (warp == 0) {
-            float a[16], er[9], ei[9];
+        // ---- pass 2 (row = k1 = warp, warp + 8; rows 0..12) + power ----
+#pragma unroll 1
+        for (int row = warp; row < 13; row += kWarps) {
+            if (row == 0) {
+                float a[16], er[9], ei[9];
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) a[n2] = sm.ex0[n2][lane];
-            codelets::w_pass2_edge<float>(a, er, ei);
+                for (int n2 = 0; n2 < 16; ++n2) a[n2] = sm.ex0[n2][lane];
+                codelets::w_pass2_edge<float>(a, er, ei);
 #pragma unroll
-            for (int k2 = 0; k2 < 9; ++k2) sm.P[25 * k2][lane] = fmaf(er[k2], er[k2], ei[k2] * ei[k2]);
-        } else if (warp < 13) {
-            float xr[16], xi[16], yr[16], yi[16];
+                for (int k2 = 0; k2 < 9; ++k2) sm.u.P[25 * k2][lane] = fmaf(er[k2], er[k2], ei[k2] * ei[k2]);
+            } else {
+                float xr[16], xi[16], yr[16], yi[16];
 #pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) {
-                const float2 v = sm.ex[warp - 1][n2][lane];
-                xr[n2] = v.x; xi[n2] = v.y;
+                for (int n2 = 0; n2 < 16; ++n2) {
+                    const float2 v = sm.ex[row - 1][n2][lane];
+                    xr[n2] = v.x; xi[n2] = v.y;
+                }
+                codelets::dft16<float>(xr, xi, yr, yi);
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2)
+                    sm.u.P[k2 < 8 ? row + 25 * k2 : 400 - row - 25 * k2][lane] = fmaf(yr[k2], yr[k2], yi[k2] * yi[k2]);
             }
-            codelets::dft16<float>(xr, xi, yr, yi);
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2)
-                sm.P[k2 < 8 ? warp + 25 * k2 : 400 - warp - 25 * k2][lane] = fmaf(yr[k2], yr[k2], yi[k2] * yi[k2]);
         }
         __syncthreads();
 
         // ---- mel + log10: lane <-> frame, so the stores along t coalesce ----
         {
-            const float* Pl = &sm.P[0][lane];
+            const float* Pl = &sm.u.P[0][lane];
             const int t = t0 + lane;
-            float v[5];
-            v[0] = mel_slot<0>(Pl, sm.melw, sm.melfirst, warp);
-            v[1] = mel_slot<1>(Pl, sm.melw, sm.melfirst, warp);
-            v[2] = mel_slot<2>(Pl, sm.melw, sm.melfirst, warp);
-            v[3] = mel_slot<3>(Pl, sm.melw, sm.melfirst, warp);
-            v[4] = mel_slot<4>(Pl, sm.melw, sm.melfirst, warp);
-            if (t < t_end) {
+#pragma unroll 1
+            for (int role = warp; role < 16; role += kWarps) {
+                float v[5];
+                v[0] = mel_slot<0>(Pl, sm.melw, sm.melfirst, role);
+                v[1] = mel_slot<1>(Pl, sm.melw, sm.melfirst, role);
+                v[2] = mel_slot<2>(Pl, sm.melw, sm.melfirst, role);
+                v[3] = mel_slot<3>(Pl, sm.melw, sm.melfirst, role);
+                v[4] = mel_slot<4>(Pl, sm.melw, sm.melfirst, role);
+                if (t < t_end) {
 #pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    out_b[(size_t)(warp + 16 * i) * T + t] = v[i];
-                    run_max = fmaxf(run_max, v[i]);
+                    for (int i = 0; i < 5; ++i) {
+                        out_b[(size_t)(role + 16 * i) * T + t] = v[i];
+                        run_max = fmaxf(run_max, v[i]);
+                    }
                 }
             }
         }
-        // the next iteration's layout pass writes xs / reads stage only; its __syncthreads orders this mel stage's
-        // reads of P before the next pass 2 overwrites it
+        __syncthreads();                            // the power spectrum is consumed: the next layout pass may overwrite it
     }
 
 #pragma unroll
@@ -381,6 +389,7 @@ int get_tables(const WTables** out) {
         STX_CUDA(cudaMalloc(&d, sizeof(WTables)));
         STX_CUDA(cudaMemcpy(d, &h, sizeof(WTables), cudaMemcpyHostToDevice));
         STX_CUDA(cudaFuncSetAttribute(w_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        STX_CUDA(cudaFuncSetAttribute(w_frames, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         g_tab[dev] = d;
     }
     *out = g_tab[dev];
@@ -393,7 +402,7 @@ inline int pick_chunk(int B, int frames, int sms) {
     long long best_cost = -1;
     for (int chunk = 64; chunk <= 512; chunk += kTile) {
         const long long ctas = (long long)B * ((frames + chunk - 1) / chunk);
-        const long long cost = ((ctas + sms - 1) / sms) * (chunk / kTile);
+        const long long cost = ((ctas + 2 * sms - 1) / (2 * sms)) * (chunk / kTile);      // two CTAs per SM
         if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = chunk; }
     }
     return best;
