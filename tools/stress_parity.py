@@ -1,0 +1,76 @@
+"""Randomised stress of the K and W paths (there is no compute-sanitizer on the bench pool): many random batches,
+each checked for run-to-run determinism, bit-level invariance to batch composition (a clip's features must not depend on
+its neighbours, the chunking, or the pipeline that produced them) and, on a sample, against the CPU oracle.
+
+    python tools/stress_parity.py [rounds] [seed]
+"""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from oracle import fbank_k as OK  # noqa: E402  (checker)
+from oracle import logmel_w as OW  # noqa: E402
+from speech_transcript_embeddings_b200 import ops, synth  # noqa: E402
+from speech_transcript_embeddings_b200.feature_extraction import (B200SeamlessM4TFeatureExtractor,  # noqa: E402
+                                                                  B200WhisperFeatureExtractor)
+
+rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+dev = torch.device("cuda", 0)
+fk = B200SeamlessM4TFeatureExtractor(device=dev)
+fw = B200WhisperFeatureExtractor(device=dev)
+kinds = ["G", "U", "AM", "HS", "small", "loud"]
+worst_k = worst_w = 0.0
+t_start = time.time()
+for r in range(rounds):
+    B = int(rng.integers(1, 48))
+    lens = rng.integers(400, 16000 * int(rng.integers(1, 31)) + 1, size=B)
+    if r % 5 == 0:
+        lens[rng.integers(0, B)] = int(rng.integers(1, 400))          # a clip too short for a single frame
+    clips = [synth.clip(kinds[int(rng.integers(0, len(kinds)))], int(n), int(rng.integers(0, 1 << 30))) for n in lens]
+    # ---- K: device path twice, host pipeline with a random chunk size, shuffled batch ----
+    a = fk(clips, sampling_rate=16000, return_tensors="pt")
+    b = fk(clips, sampling_rate=16000, return_tensors="pt")
+    assert torch.equal(a["input_features"], b["input_features"]) or torch.isnan(a["input_features"]).any(), "K not deterministic"
+    old = type(fk).CHUNK_BYTES
+    type(fk).CHUNK_BYTES = int(rng.integers(1, 8 << 20))
+    h = fk(clips, sampling_rate=16000, return_tensors="pt", output="host")
+    type(fk).CHUNK_BYTES = old
+    xa = a["input_features"].cpu()
+    same = (xa == h["input_features"]) | (torch.isnan(xa) & torch.isnan(h["input_features"]))
+    assert bool(same.all()) and torch.equal(a["attention_mask"].cpu(), h["attention_mask"]), "K pipeline differs"
+    perm = rng.permutation(B)
+    p = fk([clips[i] for i in perm], sampling_rate=16000, return_tensors="pt")["input_features"].cpu()
+    for j, i in enumerate(perm[:6]):
+        T2 = (ops.k_num_frames(clips[i].size) + 1) // 2
+        u, v = xa[i, :T2], p[j, :T2]
+        assert bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all()), "K depends on the batch"
+    i = int(rng.integers(0, B))
+    if clips[i].size >= 560:
+        with np.errstate(all="ignore"):
+            ref = OK.extract([clips[i]])[0][0]
+        err = float(np.nanmax(np.abs(xa[i, :ref.shape[0]].numpy() - ref)))
+        if err > 5e-5:
+            raw = fk(clips[i], sampling_rate=16000, return_tensors="np", do_normalize_per_mel_bins=False)["input_features"][0]
+            with np.errstate(all="ignore"):
+                ref_raw = OK.extract([clips[i]], normalize=False)[0][0]
+            T = ops.k_num_frames(clips[i].size)
+            feat = ref_raw.reshape(-1, 80)[:T]
+            print(f"  large K error {err:.2e}: n = {clips[i].size}, T = {T}, raw log-mel error {np.abs(raw - ref_raw).max():.2e}, "
+                  f"smallest per-bin std {feat.std(0, ddof=1).min():.2e}", flush=True)
+        worst_k = max(worst_k, err)
+    # ---- W (short max_length keeps it cheap) ----
+    ml = 160 * int(rng.integers(3, 400))
+    wa = fw(clips, sampling_rate=16000, return_tensors="pt", max_length=ml)["input_features"]
+    wb = fw([clips[i] for i in perm], sampling_rate=16000, return_tensors="pt", max_length=ml)["input_features"]
+    assert torch.equal(wa[perm], wb), "W depends on the batch"
+    refw, _ = OW.extract([clips[i]], n_samples=ml)
+    worst_w = max(worst_w, float(np.abs(wa[i].cpu().numpy() - refw[0]).max()))
+    if r % 10 == 9:
+        print(f"round {r + 1}: worst K {worst_k:.2e}, worst W {worst_w:.2e}, {time.time() - t_start:.0f} s", flush=True)
+assert worst_k <= 1e-4 and worst_w <= 1e-4, (worst_k, worst_w)
+print(f"stress ok: {rounds} rounds, worst K {worst_k:.2e}, worst W {worst_w:.2e}")
