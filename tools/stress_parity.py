@@ -24,7 +24,7 @@ dev = torch.device("cuda", 0)
 fk = B200SeamlessM4TFeatureExtractor(device=dev)
 fw = B200WhisperFeatureExtractor(device=dev)
 kinds = ["G", "U", "AM", "HS", "small", "loud"]
-worst_k = worst_w = 0.0
+worst_k = worst_w = worst_k_illcond = 0.0
 t_start = time.time()
 for r in range(rounds):
     B = int(rng.integers(1, 48))
@@ -60,8 +60,15 @@ for r in range(rounds):
                 ref_raw = OK.extract([clips[i]], normalize=False)[0][0]
             T = ops.k_num_frames(clips[i].size)
             feat = ref_raw.reshape(-1, 80)[:T]
-            print(f"  large K error {err:.2e}: n = {clips[i].size}, T = {T}, raw log-mel error {np.abs(raw - ref_raw).max():.2e}, "
-                  f"smallest per-bin std {feat.std(0, ddof=1).min():.2e}", flush=True)
+            raw_err, std_min = float(np.abs(raw - ref_raw).max()), float(feat.std(0, ddof=1).min())
+            print(f"  large K error {err:.2e}: n = {clips[i].size}, T = {T}, raw log-mel error {raw_err:.2e}, "
+                  f"smallest per-bin std {std_min:.2e}", flush=True)
+            if std_min < 0.05:
+                # a handful of frames with a near-constant mel bin: 1/sqrt(var + 1e-7) amplifies float32 rounding of the
+                # raw log-mel by up to 3162 in the reference itself; gate the raw values instead
+                assert raw_err <= 2e-5, raw_err
+                worst_k_illcond = max(worst_k_illcond, err)
+                err = 0.0
         worst_k = max(worst_k, err)
     # ---- W (short max_length keeps it cheap) ----
     ml = 160 * int(rng.integers(3, 400))
@@ -73,4 +80,5 @@ for r in range(rounds):
     if r % 10 == 9:
         print(f"round {r + 1}: worst K {worst_k:.2e}, worst W {worst_w:.2e}, {time.time() - t_start:.0f} s", flush=True)
 assert worst_k <= 1e-4 and worst_w <= 1e-4, (worst_k, worst_w)
-print(f"stress ok: {rounds} rounds, worst K {worst_k:.2e}, worst W {worst_w:.2e}")
+print(f"stress ok: {rounds} rounds, worst K {worst_k:.2e} (ill-conditioned clips, raw values gated: {worst_k_illcond:.2e}), "
+      f"worst W {worst_w:.2e}")
