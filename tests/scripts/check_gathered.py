@@ -1,6 +1,6 @@
 """Multi-GPU check + timing of the fused all-gather + N x M cosine path (run under torchrun, >= 2 GPUs):
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_gathered.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/scripts/check_gathered.py
 
 Every rank checks its stripe against the float64 oracle (checker only) and against the NCCL all-gather path, for
 equal and ragged shards; rank 0 prints one JSON line with both timings (CUDA events, max over ranks).

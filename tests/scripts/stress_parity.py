@@ -2,7 +2,7 @@
 each checked for run-to-run determinism, bit-level invariance to batch composition (a clip's features must not depend on
 its neighbours, the chunking, or the pipeline that produced them) and, on a sample, against the CPU oracle.
 
-    python tools/stress_parity.py [rounds] [seed]
+    python tests/scripts/stress_parity.py [rounds] [seed]
 """
 import sys
 import time
