@@ -40,7 +40,7 @@ CLIPS_PER_BATCH = 64
 POOL_BATCHES = 4                       # distinct batches rotated so that inputs + outputs >> 126 MB of L2
 K_BYTES_PER_CLIP = 4 * 480000 + 1499 * 160 * 4 + 1499 * 4       # 2 885 356 B per 30 s clip
 W_BYTES_PER_CLIP = 4 * 480000 + 80 * 3000 * 4                   # 2 880 000 B
-K_F64_FLOP_PER_FRAME = 9400.0          # FP64 instructions (counted as flop) per frame, frame chain + FFT
+K_F64_FLOP_PER_FRAME = 7600.0          # FP64 instructions (counted as flop) per frame, frame chain + FFT (lazy-scale codelets)
 FALLBACK_HBM_GBS = 6650.0
 
 

@@ -5,10 +5,13 @@ There is no fallback: if the library is missing or a call fails, an exception is
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libstx_b200.so"
+# STX_B200_LIB: development override, an alternative BUILD OF THE SAME LIBRARY (A/B timing of kernel variants,
+# tools/time_kernels.py).  It is still the CUDA library or nothing: a missing file raises like the default path does.
+LIB_PATH = Path(os.environ.get("STX_B200_LIB") or Path(__file__).resolve().parent / "libstx_b200.so")
 
 # symbol -> (restype, argtypes); lists every function include/stx_b200.h declares
 _SIGNATURES = {

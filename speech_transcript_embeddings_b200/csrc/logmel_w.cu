@@ -244,8 +244,10 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         }
 
         // ---- window + pass 1 (role = n2 = warp, warp + 8) ----
-#pragma unroll 1
-        for (int role = warp; role < 16; role += kWarps) {
+        // two roles per warp, written out (not a loop): `warp` is provably warp-uniform, a loop-carried role is not, and only
+        // a provably uniform index lets the window / twiddle reads go through the uniform datapath instead of queueing
+        // register-indexed constant loads in the MIO with the shared-memory traffic
+        auto pass1 = [&](const int role) {
             const float* X = sm.u.xs + kXRow * lane + role;
             float y[25], re[13], im[13];
 #pragma unroll
@@ -254,10 +256,15 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             sm.ex0[role][lane] = re[0];
 #pragma unroll
             for (int k1 = 1; k1 < 13; ++k1) {
+                // the codelet leaves im[k1] short of a constant factor (its last butterfly's sine).  Folding the factor into
+                // a four-entry twiddle costs more in constant loads than the multiply does (measured: 130 vs 126 us on cfg2)
                 const float2 t = cw_tw[role][k1];
-                sm.ex[k1 - 1][role][lane] = make_float2(fmaf(re[k1], t.x, -(im[k1] * t.y)), fmaf(re[k1], t.y, im[k1] * t.x));
+                const float imk = im[k1] * float(codelets::w_pass1_im_scale_of(k1));
+                sm.ex[k1 - 1][role][lane] = make_float2(fmaf(re[k1], t.x, -(imk * t.y)), fmaf(re[k1], t.y, imk * t.x));
             }
-        }
+        };
+        pass1(warp);
+        pass1(warp + kWarps);
         __syncthreads();                            // exchange complete; xs is dead, its storage becomes the power spectrum
 
         // ---- pass 2 (row = k1 = warp, warp + 8; rows 0..12) + power ----

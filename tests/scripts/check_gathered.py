@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = Path(__file__).resolve().parent.parent
+ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from oracle import cosine as OC  # noqa: E402  (checker)
 from speech_transcript_embeddings_b200 import scoring, synth  # noqa: E402

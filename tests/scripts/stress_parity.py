@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from oracle import fbank_k as OK  # noqa: E402  (checker)
 from oracle import logmel_w as OW  # noqa: E402
 from speech_transcript_embeddings_b200 import ops, synth  # noqa: E402

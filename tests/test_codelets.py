@@ -42,7 +42,7 @@ template <typename T> static void run_w_pass1(const T* in, T* out) {
     for (int i = 0; i < 25; ++i) y[i] = in[i];
     for (int i = 0; i < 13; ++i) re[i] = im[i] = 0;
     w_pass1<T>(y, re, im);
-    for (int i = 0; i < 13; ++i) { out[2 * i] = re[i]; out[2 * i + 1] = im[i]; }
+    for (int i = 0; i < 13; ++i) { out[2 * i] = re[i]; out[2 * i + 1] = im[i] * T(w_pass1_im_scale[i]); }   // exported scale
 }
 template <typename T> static void run_w_pass2_edge(const T* in, T* out) {
     T a[16], er[9], ei[9];

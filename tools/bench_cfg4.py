@@ -1,0 +1,145 @@
+"""cfg4 (BASELINE.json configs[3]): 10 000 synthetic clip-hours through the front end, clips sharded over the GPUs of
+one box, no data-path collective.
+
+    python tools/bench_cfg4.py [--hours 10000] [--recipe K|W] [--pool 1024] [--batch 128]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 \
+        tools/bench_cfg4.py
+
+3.6e7 audio-seconds of float32 PCM are 2.3 TB and cannot be stored, so every rank cycles a device-resident pool of
+`--pool` x 30 s class-G clips (1.97 GB at 1024: far larger than the 126 MB L2, so every load comes from HBM), generated on
+the device from a per-rank seed, in calls of `--batch` clips; the outputs are overwritten in a ring of two buffers.  Each
+rank processes hours / world of audio.  Timed with CUDA events on the launching stream between barriers, max over ranks.
+
+Integrity without an oracle (size-independent properties): (1) per-clip checksums of the first and of the last pass over
+the pool are bit-identical (run-to-run determinism under load); (2) a sample of clips recomputed alone, in a batch of one,
+is bit-identical to its rows in the big batches (a clip's features do not depend on its neighbours: the statistics are
+integer sums); (3) masks are all ones for these full-length clips; (4) every normalised mel bin of a sampled clip has
+mean 0 and variance 1 over the clip's frames (recipe K) / the maximum of a clip is exactly (max+4)/4-consistent with
+the max-8 clamp (recipe W: min >= max - 2).
+"""
+import argparse
+import json
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from speech_transcript_embeddings_b200 import _lib, ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--hours", type=float, default=10000.0)
+ap.add_argument("--recipe", choices=["K", "W"], default="K")
+ap.add_argument("--pool", type=int, default=1024)
+ap.add_argument("--batch", type=int, default=128)
+args = ap.parse_args()
+
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+n = 480000
+P, B = args.pool, args.batch
+assert P % B == 0
+g = torch.Generator(device=dev).manual_seed(4000 + rank)
+pcm = torch.empty(P * n, dtype=torch.float32, device=dev)
+for i in range(0, P, 64):                                   # generated in slices: randn's temporaries stay small
+    pcm[i * n:(i + 64) * n] = 0.1 * torch.randn(64 * n, generator=g, device=dev)
+off = (torch.arange(B, dtype=torch.int64, device=dev) * n)
+lens = torch.full((B,), n, dtype=torch.int32, device=dev)
+T = ops.k_num_frames(n)
+T_pad = T + (T & 1)
+if args.recipe == "K":
+    ring = [torch.empty((B, T_pad // 2, 160), dtype=torch.float32, device=dev) for _ in range(2)]
+    masks = [torch.empty((B, T_pad // 2), dtype=torch.int32, device=dev) for _ in range(2)]
+
+    def call(i, slot):
+        ops.fbank_k(pcm[i * B * n:(i + 1) * B * n], off, lens, n, T_pad, out=ring[slot], mask=masks[slot])
+else:
+    ring = [torch.empty((B, 80, 3000), dtype=torch.float32, device=dev) for _ in range(2)]
+    masks = None
+
+    def call(i, slot):
+        ops.logmel_w(pcm[i * B * n:(i + 1) * B * n], off, lens, n, out=ring[slot])
+
+calls_per_pass = P // B
+audio_s_rank = args.hours * 3600.0 / world
+passes = max(2, int(np.ceil(audio_s_rank / (P * 30.0))))
+
+
+def checksums():
+    """[P] int64: a bit-level checksum of every clip's features (sum of the raw float32 words as integers)."""
+    cs = torch.empty(P, dtype=torch.int64, device=dev)
+    for i in range(calls_per_pass):
+        call(i, i & 1)
+        cs[i * B:(i + 1) * B] = ring[i & 1].view(torch.int32).view(B, -1).to(torch.int64).sum(dim=1)
+    return cs
+
+
+first = checksums()                                          # also the warm-up pass
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+n0 = _lib.launch_count()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for p in range(passes):
+    for i in range(calls_per_pass):
+        call(i, i & 1)
+e1.record()
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+launches = _lib.launch_count() - n0
+ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+last = checksums()
+ok_det = bool(torch.equal(first, last))
+
+# batch invariance + per-clip properties on a sample
+ok_inv, ok_prop = True, True
+off1 = torch.zeros(1, dtype=torch.int64, device=dev)
+len1 = torch.full((1,), n, dtype=torch.int32, device=dev)
+for j in (0, B - 1, P // 2 + 3, P - 1):
+    i, r = divmod(j, B)
+    call(i, 0)
+    if args.recipe == "K":
+        o1 = torch.empty((1, T_pad // 2, 160), dtype=torch.float32, device=dev)
+        m1 = torch.empty((1, T_pad // 2), dtype=torch.int32, device=dev)
+        ops.fbank_k(pcm[j * n:(j + 1) * n], off1, len1, n, T_pad, out=o1, mask=m1)
+        ok_inv &= bool(torch.equal(o1[0], ring[0][r])) and bool((masks[0][r, :T // 2] == 1).all())
+        x = ring[0][r].reshape(-1, 80)[:T].double()
+        ok_prop &= bool(x.mean(0).abs().max() < 1e-5) and bool((x.var(0, unbiased=True) - 1).abs().max() < 1e-4)
+    else:
+        o1 = torch.empty((1, 80, 3000), dtype=torch.float32, device=dev)
+        ops.logmel_w(pcm[j * n:(j + 1) * n], off1, len1, n, out=o1)
+        ok_inv &= bool(torch.equal(o1[0], ring[0][r]))
+        ok_prop &= bool(ring[0][r].min() >= ring[0][r].max() - 2.0 - 1e-6)
+flags = torch.tensor([int(ok_det), int(ok_inv), int(ok_prop)], device=dev)
+if world > 1:
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+
+if rank == 0:
+    secs = float(ms.item()) * 1e-3
+    audio_s = world * passes * P * 30.0
+    print(json.dumps({
+        "workload": f"cfg4: {args.hours:.0f} clip-hours, recipe {args.recipe}, {world} GPU(s), pool {P} x 30 s per GPU "
+                    f"({P * n * 4 / 1e9:.2f} GB), calls of {B} clips, {passes} passes per GPU",
+        "audio_hours_processed": audio_s / 3600.0, "seconds": secs, "audio_s_per_s": audio_s / secs,
+        "seconds_for_10k_clip_hours": 3.6e7 / (audio_s / secs), "n_gpus": world, "gpu_launches": launches,
+        "deterministic_across_passes": bool(flags[0].item()), "batch_invariant": bool(flags[1].item()),
+        "per_clip_properties": bool(flags[2].item()),
+    }), flush=True)
+if world > 1:
+    dist.destroy_process_group()
+if not bool(flags.min().item()):
+    sys.exit(1)

@@ -35,16 +35,20 @@ OUT = ROOT / "speech_transcript_embeddings_b200" / "csrc" / "codelets.cuh"
 
 
 class Graph:
-    """Real-valued expression DAG.  A value is a node id, or None for an exact zero."""
+    """Real-valued expression DAG whose values carry a LAZY SCALE: a value is None (an exact zero) or a pair
+    (scale, node) standing for scale * node.  Multiplying by a constant only changes the scale; an addition of two
+    values with different scales becomes ONE fused multiply-add, s1 * (n1 + (s2 / s1) * n2), whose scale stays pending
+    and is absorbed by the next addition (or paid as one multiply at an output).  A complex twiddle multiplication
+    followed by a butterfly therefore costs 6 FMAs instead of 4 + 4 operations (the tangent form of the twiddle falls
+    out of the rule), and negations never cost anything."""
 
     def __init__(self):
-        self.nodes = []          # (op, a, b)  op in {in, add, sub, mul, neg}
+        self.nodes = []          # ("in", name) | ("add", a, b) | ("sub", a, b) | ("fma", c, a, b) = c * a + b
         self.memo = {}
 
-    def _mk(self, op, a, b=None):
-        key = (op, a, b)
-        if op == "add" and a > b:
-            key = (op, b, a)
+    def _mk(self, *key):
+        if key[0] == "add" and key[1] > key[2]:
+            key = ("add", key[2], key[1])
         hit = self.memo.get(key)
         if hit is not None:
             return hit
@@ -53,62 +57,42 @@ class Graph:
         return len(self.nodes) - 1
 
     def inp(self, name):
-        return self._mk("in", name)
+        return (1.0, self._mk("in", name))
 
-    def is_neg(self, a):
-        return a is not None and self.nodes[a][0] == "neg"
+    @staticmethod
+    def neg(a):
+        return None if a is None else (-a[0], a[1])
 
-    def neg(self, a):
-        if a is None:
+    @staticmethod
+    def mul(c, a):
+        if a is None or c == 0.0:
             return None
-        if self.is_neg(a):
-            return self.nodes[a][1]
-        if self.nodes[a][0] == "mul":
-            return self.mul(-self.nodes[a][1], self.nodes[a][2])
-        if self.nodes[a][0] == "sub":
-            return self._mk("sub", self.nodes[a][2], self.nodes[a][1])
-        return self._mk("neg", a)
+        return (c * a[0], a[1])
 
     def add(self, a, b):
         if a is None:
             return b
         if b is None:
             return a
-        if self.is_neg(b):
-            return self.sub(a, self.nodes[b][1])
-        if self.is_neg(a):
-            return self.sub(b, self.nodes[a][1])
-        return self._mk("add", a, b)
+        (s1, n1), (s2, n2) = a, b
+        if n1 == n2:
+            return None if s1 + s2 == 0.0 else (s1 + s2, n1)
+        if s1 == s2:
+            return (s1, self._mk("add", n1, n2))
+        if s1 == -s2:
+            return (s1, self._mk("sub", n1, n2))
+        # pivot: a unit scale if there is one (the result then needs no multiply at an output), else the larger one
+        # (|ratio| <= 1: the tangent, not the cotangent)
+        if abs(s2) == 1.0 and abs(s1) != 1.0 or (abs(s1) != 1.0 and abs(s2) > abs(s1)):
+            s1, n1, s2, n2 = s2, n2, s1, n1
+        return (s1, self._mk("fma", s2 / s1, n2, n1))
 
     def sub(self, a, b):
-        if b is None:
-            return a
-        if a is None:
-            return self.neg(b)
-        if a == b:
-            return None
-        if self.is_neg(b):
-            return self.add(a, self.nodes[b][1])
-        if self.is_neg(a):
-            return self.neg(self.add(self.nodes[a][1], b))
-        return self._mk("sub", a, b)
-
-    def mul(self, c, a):
-        if a is None or c == 0.0:
-            return None
-        if c == 1.0:
-            return a
-        if c == -1.0:
-            return self.neg(a)
-        if self.is_neg(a):
-            return self.mul(-c, self.nodes[a][1])
-        if self.nodes[a][0] == "mul":
-            return self.mul(c * self.nodes[a][1], self.nodes[a][2])
-        return self._mk("mul", float(c), a)
+        return self.add(a, self.neg(b))
 
 
 class Cx:
-    """Complex value over a Graph: (re, im) node ids."""
+    """Complex value over a Graph: (re, im) lazily scaled values."""
     __slots__ = ("g", "re", "im")
 
     def __init__(self, g, re, im):
@@ -135,18 +119,6 @@ class Cx:
     def cmul(self, w: complex):
         c, s = _snap(w.real), _snap(w.imag)
         g = self.g
-        if s == 0.0:
-            return self.scale(c)
-        if c == 0.0:
-            return Cx(g, g.mul(-s, self.im), g.mul(s, self.re))
-        if abs(abs(c) - abs(s)) < 1e-15:
-            # c (a + jb)(1 + j s/c): one add and one multiply per component
-            sg = 1.0 if (c > 0) == (s > 0) else -1.0
-            if sg > 0:
-                re, im = g.sub(self.re, self.im), g.add(self.re, self.im)
-            else:
-                re, im = g.add(self.re, self.im), g.sub(self.im, self.re)
-            return Cx(g, g.mul(c, re), g.mul(c, im))
         return Cx(g, g.sub(g.mul(c, self.re), g.mul(s, self.im)), g.add(g.mul(s, self.re), g.mul(c, self.im)))
 
 
@@ -182,6 +154,11 @@ def butterfly(xs):
         t0, t1 = xs[0] + xs[2], xs[0] - xs[2]
         t2, t3 = xs[1] + xs[3], xs[1] - xs[3]
         return [t0 + t2, t1 + t3.mul_mj(), t0 - t2, t1 + t3.mul_j()]
+    if r == 3:
+        c, sn = -0.5, math.sin(2 * math.pi / 3)
+        t1, t2 = xs[1] + xs[2], (xs[1] - xs[2]).scale(sn)
+        m1 = xs[0] + t1.scale(c)
+        return [xs[0] + t1, m1 + t2.mul_mj(), m1 + t2.mul_j()]
     if r == 5:
         c1, c2 = math.cos(2 * math.pi / 5), math.cos(4 * math.pi / 5)
         s1, s2 = math.sin(2 * math.pi / 5), math.sin(4 * math.pi / 5)
@@ -196,33 +173,40 @@ def butterfly(xs):
 
 
 def dft(xs):
-    """Forward DFT of a list of Cx by decimation in time; real inputs produce shared conjugate halves."""
+    """Forward DFT of a list of Cx by decimation in time.  Real inputs: only the columns k <= m/2 of the last stage are
+    computed (with all their outputs); every other output is the conjugate of one of those."""
     n = len(xs)
     if n == 1:
         return list(xs)
-    if n in (2, 4, 5):
+    real = is_real(xs)
+    if n in (2, 3, 4, 5):
         out = butterfly(xs)
     else:
-        r = 4 if n % 4 == 0 else 2 if n % 2 == 0 else 5
+        r = 4 if n % 4 == 0 else 2 if n % 2 == 0 else 5 if n % 5 == 0 else 3
         assert n % r == 0, n
         m = n // r
         subs = [dft(xs[q::r]) for q in range(r)]
-        out = [None] * n
-        real = is_real(xs)
-        tw = {}
+        out = [NOT_COMPUTED] * n
         for k in range(m):
-            if real and r in (2, 4) and k > m - k:
-                # real input: sub[q][m-k'] = conj(sub[q][k'])  =>  twiddled value = W_r^q conj(twiddled value of column m-k)
-                tw[k] = [tw[m - k][q].conj().cmul(w(r, q)) for q in range(r)]
-            else:
-                tw[k] = [subs[q][k].cmul(w(n, q * k)) for q in range(r)]
-            col = butterfly(tw[k])
+            if real and 2 * k > m:
+                continue
+            col = butterfly([subs[q][k].cmul(w(n, q * k)) for q in range(r)])
             for j in range(r):
                 out[k + m * j] = col[j]
-    if is_real(xs):
+        for i in range(n):
+            if out[i] is NOT_COMPUTED:
+                out[i] = out[(n - i) % n].conj()
+    if real:
+        # exact symmetry: share the nodes (and make the imaginary parts of bins 0 and n/2 exact zeros)
         for k in range(n // 2 + 1, n):
             out[k] = out[n - k].conj()
+        out[0] = Cx(out[0].g, out[0].re, None)
+        if n % 2 == 0:
+            out[n // 2] = Cx(out[0].g, out[n // 2].re, None)
     return out
+
+
+NOT_COMPUTED = object()
 
 
 class Codelet:
@@ -231,6 +215,8 @@ class Codelet:
         self.g = Graph()
         self.params = []         # (c type prefix, name, length, is_output)
         self.outputs = []        # (lvalue, node or None)
+        self.exported = {}       # array name -> [scale per index]: pending output scales the CALLER folds into its own
+                                 # constants (the twiddle table) instead of the codelet paying a multiply for them
 
     def real_in(self, name, count, nonzero=None):
         self.params.append(("const T", name, count, False))
@@ -249,88 +235,96 @@ class Codelet:
     def emit_out(self, lvalue, node):
         self.outputs.append((lvalue, node))
 
+    def emit_out_scaled(self, array, index, count, node):
+        """Output array[index] WITHOUT its pending scale; the scale goes to the constexpr table <codelet>_<array>_scale."""
+        tab = self.exported.setdefault(array, [1.0] * count)
+        if node is not None:
+            tab[index] = abs(node[0])
+            node = (1.0 if node[0] > 0 else -1.0, node[1])
+        self.outputs.append((f"{array}[{index}]", node))
+
     # ---- evaluation / emission ----
     def _reachable(self):
         need = set()
-        stack = [n for _, n in self.outputs if n is not None]
+        stack = [v[1] for _, v in self.outputs if v is not None]
         while stack:
             i = stack.pop()
             if i in need:
                 continue
             need.add(i)
-            op, a, b = self.g.nodes[i]
-            if op in ("add", "sub"):
-                stack += [a, b]
-            elif op == "mul":
-                stack.append(b)
-            elif op == "neg":
-                stack.append(a)
+            node = self.g.nodes[i]
+            if node[0] in ("add", "sub"):
+                stack += [node[1], node[2]]
+            elif node[0] == "fma":
+                stack += [node[2], node[3]]
         return sorted(need)
 
     def op_count(self):
-        return sum(1 for i in self._reachable() if self.g.nodes[i][0] != "in")
+        """Arithmetic instructions: one per add / sub / fma node plus one multiply per output whose pending scale is
+        not +-1 (a sign is folded into the consumer)."""
+        ops = sum(1 for i in self._reachable() if self.g.nodes[i][0] != "in")
+        return ops + sum(1 for _, v in self.outputs if v is not None and abs(v[0]) != 1.0)
 
-    def fused_op_count(self):
-        """Ops after mul+add contraction (a multiply whose only consumer is one add/sub becomes an FMA)."""
-        reach = self._reachable()
-        uses = {}
-        for i in reach:
-            op, a, b = self.g.nodes[i]
-            for s_ in ((a, b) if op in ("add", "sub") else (b,) if op == "mul" else (a,) if op == "neg" else ()):
-                uses.setdefault(s_, []).append(i)
-        for _, n_ in self.outputs:
-            if n_ is not None:
-                uses.setdefault(n_, []).append(-1)
-        fused, taken = 0, set()
-        for i in reach:
-            if self.g.nodes[i][0] == "mul" and len(uses.get(i, [])) == 1 and uses[i][0] >= 0:
-                u = uses[i][0]
-                if self.g.nodes[u][0] in ("add", "sub") and u not in taken:
-                    taken.add(u)
-                    fused += 1
-        return self.op_count() - fused
+    def fma_count(self):
+        return sum(1 for i in self._reachable() if self.g.nodes[i][0] == "fma")
 
     def evaluate(self, env):
         """env: {"name[i]": value}; returns {lvalue: value} in float64 (numpy scalars)."""
         val = {}
         for i in self._reachable():
-            op, a, b = self.g.nodes[i]
-            if op == "in":
-                val[i] = np.float64(env[a])
-            elif op == "add":
-                val[i] = val[a] + val[b]
-            elif op == "sub":
-                val[i] = val[a] - val[b]
-            elif op == "mul":
-                val[i] = np.float64(a) * val[b]
+            node = self.g.nodes[i]
+            if node[0] == "in":
+                val[i] = np.float64(env[node[1]])
+            elif node[0] == "add":
+                val[i] = val[node[1]] + val[node[2]]
+            elif node[0] == "sub":
+                val[i] = val[node[1]] - val[node[2]]
             else:
-                val[i] = -val[a]
-        return {lv: (val[n] if n is not None else np.float64(0.0)) for lv, n in self.outputs}
+                val[i] = np.float64(node[1]) * val[node[2]] + val[node[3]]
+        res = {lv: (np.float64(v[0]) * val[v[1]] if v is not None else np.float64(0.0)) for lv, v in self.outputs}
+        for array, tab in self.exported.items():
+            for i, sc in enumerate(tab):
+                if f"{array}[{i}]" in res:
+                    res[f"{array}[{i}]"] = res[f"{array}[{i}]"] * np.float64(sc)
+        return res
 
     def source(self):
-        lines = [f"// {self.doc}  [{self.op_count()} arithmetic ops]",
+        lines = [f"// {self.doc}  [{self.op_count()} arithmetic ops, {self.fma_count()} of them FMAs]",
                  "template <typename T>",
                  f"__host__ __device__ __forceinline__ void {self.name}(" +
                  ", ".join(f"{ty} (&{nm})[{cnt}]" for ty, nm, cnt, _ in self.params) + ") {"]
         name = {}
         for i in self._reachable():
-            op, a, b = self.g.nodes[i]
-            if op == "in":
-                name[i] = a
+            node = self.g.nodes[i]
+            if node[0] == "in":
+                name[i] = node[1]
                 continue
             name[i] = f"t{i}"
-            if op == "add":
-                rhs = f"{name[a]} + {name[b]}"
-            elif op == "sub":
-                rhs = f"{name[a]} - {name[b]}"
-            elif op == "mul":
-                rhs = f"T({a!r}) * {name[b]}"
+            if node[0] == "add":
+                rhs = f"{name[node[1]]} + {name[node[2]]}"
+            elif node[0] == "sub":
+                rhs = f"{name[node[1]]} - {name[node[2]]}"
             else:
-                rhs = f"-{name[a]}"
+                rhs = f"fma_(T({node[1]!r}), {name[node[2]]}, {name[node[3]]})"
             lines.append(f"    const T t{i} = {rhs};")
-        for lv, n in self.outputs:
-            lines.append(f"    {lv} = {name[n] if n is not None else 'T(0)'};")
+        for lv, v in self.outputs:
+            if v is None:
+                rhs = "T(0)"
+            elif v[0] == 1.0:
+                rhs = name[v[1]]
+            elif v[0] == -1.0:
+                rhs = f"-{name[v[1]]}"
+            else:
+                rhs = f"T({v[0]!r}) * {name[v[1]]}"
+            lines.append(f"    {lv} = {rhs};")
         lines.append("}")
+        for array, tab in self.exported.items():
+            lines.append(f"// true value of {array}[k] = {self.name}_{array}_scale[k] * (what {self.name} writes): fold it into the next constant")
+            lines.append(f"constexpr double {self.name}_{array}_scale[{len(tab)}] = {{" + ", ".join(repr(v) for v in tab) + "};")
+            lines.append(f"__host__ __device__ constexpr double {self.name}_{array}_scale_of(int k) {{   // usable in device code")
+            lines.append(f"    constexpr double t[{len(tab)}] = {{" + ", ".join(repr(v) for v in tab) + "};")
+            lines.append("    return t[k];")
+            lines.append("}")
         return "\n".join(lines)
 
 
@@ -418,14 +412,14 @@ def make_k_pass2_edge():
 
 
 def make_w_pass1():
-    c = Codelet("w_pass1", "recipe W pass 1: real DFT-25 of y[0..24] -> re/im[k1], k1 = 0..12 (im[0] = 0 is not written)")
+    c = Codelet("w_pass1", "recipe W pass 1: real DFT-25 of y[0..24] -> re[k1], im[k1] / w_pass1_im_scale[k1], k1 = 0..12 (im[0] = 0 is not written)")
     xs = c.real_in("y", 25)
     c.out_arrays(("re", 13), ("im", 13))
     ys = dft(xs)
     for k in range(13):
         c.emit_out(f"re[{k}]", ys[k].re)
         if k:
-            c.emit_out(f"im[{k}]", ys[k].im)
+            c.emit_out_scaled("im", k, 13, ys[k].im)
 
     def check(rng):
         y = rng.standard_normal(25)
@@ -464,8 +458,13 @@ HEADER = """// GENERATED by tools/gen_codelets.py -- do not edit; re-run the gen
 #define __forceinline__ inline
 #endif
 
+#include <cmath>
+
 namespace stx {
 namespace codelets {
+
+__host__ __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
 
 """
 
@@ -477,7 +476,7 @@ def main():
         c, check = make()
         err = max(check(rng) for _ in range(8))
         assert err < 1e-13, (c.name, err)
-        print(f"{c.name:14s} {c.op_count():4d} ops ({c.fused_op_count()} after FMA contraction)   max |err| vs numpy.fft = {err:.1e}", file=sys.stderr)
+        print(f"{c.name:14s} {c.op_count():4d} ops ({c.fma_count()} FMAs)   max |err| vs numpy.fft = {err:.1e}", file=sys.stderr)
         parts.append(c.source())
         parts.append("\n\n")
     parts.append("}  // namespace codelets\n}  // namespace stx\n")
