@@ -127,6 +127,18 @@ __device__ __forceinline__ float ln_pos(float x) {
     return fmaf(e, ln2_hi, fmaf(l2, ln2, e * ln2_lo));
 }
 
+// float64 -> float32 of a power-spectrum value on the integer pipe.  F2F.F32.F64 is a quarter-rate XU instruction and the
+// frame-per-lane kernel runs its phases in lockstep, so the 256 conversions per frame cost ~5 % of the tile time.  The value
+// is a non-negative finite double far below 2^128: re-bias the exponent (1023 -> 127) and funnel-shift the top 23 mantissa
+// bits into place.  Truncation instead of round-to-nearest (<= 1 float32 ulp, 1.2e-7 relative on a value whose LOGARITHM
+// is compared at 1e-4); anything below 2^-126 (exact zeros: digital silence) becomes a denormal <= 7 * 2^-149, i.e. zero for
+// the mel floor that follows.
+__device__ __forceinline__ float power_to_f32(double p) {
+    const unsigned hi = (unsigned)__double2hiint(p), lo = (unsigned)__double2loint(p);
+    const unsigned h = max(hi, 0x38000000u) - 0x38000000u;
+    return __uint_as_float(__funnelshift_l(lo, h, 3));
+}
+
 // ---- mbarrier + 1-D bulk copy (TMA) ---------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 // Shared-memory loads that keep their program order (volatile asm): all 16 warps of the CTA issue their exchange loads
@@ -346,7 +358,7 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             double c = 0.0;
             auto put = [&](int bin, double xr, double xi, double2 wh) {
                 const double a = fma(-c, wh.x, xr), bb = fma(-c, wh.y, xi);
-                sm.u.P[bin][lane] = (float)fma(a, a, bb * bb);
+                sm.u.P[bin][lane] = power_to_f32(fma(a, a, bb * bb));
             };
             if (warp == 0) {
                 double a[16], r[16];
