@@ -253,9 +253,12 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     const int sbin = tid % kMel, srow = tid / kMel;
     unsigned parity = 0, cparity = 0;
 
-    for (int t0 = t_begin; t0 < t_end; t0 += kTile) {
+    // convert(tc): staged PCM of the tile at frame tc -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161.  It runs in the
+    // SAME phase as the previous tile's store / statistics (d aliases the power spectrum, which is dead by then), so that its
+    // LDS -> F2F -> DFMA -> STS chains overlap the global stores, and a tile costs four CTA barriers instead of five.
+    auto convert = [&](const int tc) {
         // ---- convert: staged PCM -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161 ----
-        const int s0 = t0 * kHop;
+        const int s0 = tc * kHop;
         const StageRange sr = stage_range(s0, n, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         auto sample = [&](int g) -> float {          // x[g] of this clip, 0 outside
@@ -294,18 +297,20 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             if (tid < kTile)
                 sm.xb[tid] = 0.97 * ((double)sample(s0 + tid * kHop + kFrame - 1) - (double)sample(s0 + tid * kHop - 1));
         }
-        __syncthreads();                            // d ready; staging is free again
-
-        // next tile's PCM lands while this one is transformed
-        if (tid == 0 && t0 + kTile < t_end) {
-            const StageRange nx = stage_range(s0 + kTile * kHop, n, aligned);
+    };
+    auto prefetch = [&](const int tn) {             // PCM of the tile at frame tn lands while the tile before it is transformed
+        if (tid == 0 && tn < t_end) {
+            const int sn = tn * kHop;
+            const StageRange nx = stage_range(sn, n, aligned);
             if (nx.hi > nx.lo) {
                 mbar_expect_tx(&sm.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
-                bulk_g2s(sm.stage + (nx.lo - (s0 + kTile * kHop - kLead)), clip + nx.lo,
-                         (unsigned)(nx.hi - nx.lo) * 4u, &sm.mbar);
+                bulk_g2s(sm.stage + (nx.lo - (sn - kLead)), clip + nx.lo, (unsigned)(nx.hi - nx.lo) * 4u, &sm.mbar);
             }
         }
-
+    };
+    // the first trip (t0 = t_begin - kTile) only converts the first tile: ONE copy of every phase in the code
+    for (int t0 = t_begin - kTile; t0 < t_end; t0 += kTile) {
+      if (t0 >= t_begin) {
         // ---- window + pass 1 (warp = n2) ----
         {
             const double* D = sm.u.d + kDRow * lane + warp;
@@ -423,9 +428,12 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 }
             }
         }
-        // the next iteration's conversion pass only touches d / xb / stage; its __syncthreads orders these
-        // reads of the staged rows before pass 1 overwrites the exchange area, and the mel stage's reads of the
-        // power spectrum (aliased with d) are all before the __syncthreads above
+        // the next tile's conversion only touches d / xb / stage: the mel stage's reads of the power spectrum (aliased with
+        // d) are all before the __syncthreads above, and xb / cval of this tile were consumed in pass 2
+      }
+        if (t0 + kTile < t_end) convert(t0 + kTile);
+        __syncthreads();                            // d ready, staging free again; staged rows read before pass 1 rewrites them
+        prefetch(t0 + 2 * kTile);
     }
 
     // ---- per-chunk statistics: ordered reduction over the 6 row groups ----
