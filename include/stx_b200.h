@@ -197,6 +197,30 @@ int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int
                             const int32_t* h_counts, int m_cap, void* const* h_peer_symm, void* d_multicast,
                             uint32_t epoch, float* d_S, void* d_ws, size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Resampling to the model rate on the device: the step BEFORE the log-mel path.
+ * Replaces  audio_array = librosa.resample(audio_array, orig_sr=orig_sr, target_sr=16000)  (R/processor.py:82-86)
+ * with the arithmetic of librosa's res_type="polyphase" = scipy.signal.resample_poly(y, up, down) with its default
+ * Kaiser(5.0) low-pass of 20 * max(up, down) + 1 taps, and librosa's fix_length to ceil(n * target_sr / orig_sr)
+ * samples.  (The reference's default res_type "soxr_hq" lives in the soxr C library, which cannot be restated or
+ * pinned offline: see oracle/resample.py and INTEGRATION.md.)
+ *
+ *   stx_resample_plan    host only: up = target_sr / gcd, down = orig_sr / gcd, taps per polyphase branch, the number of
+ *                        leading outputs scipy removes, the padded filter length (any pointer may be NULL)
+ *   stx_resample_filter  host only: the padded float32 filter scipy hands to upfirdn -> h_out[0 .. return value)
+ *   stx_resample_poly    d_in packed float32 PCM at orig_sr (clip b at d_in_offsets[b], d_in_lengths[b] samples);
+ *                        d_out packed PCM at target_sr: clip b at d_out_offsets[b] with
+ *                        d_out_lengths[b] = ceil(d_in_lengths[b] * up / down) samples (the caller lays the output out;
+ *                        max_out_length = max_b d_out_lengths[b]);  d_peaks (optional, [B]) receives max(1, max|y|)
+ *                        per clip, the divisor of R/processor.py:91-92, reduced in the same pass.
+ * ------------------------------------------------------------------------------------------- */
+int stx_resample_plan(int orig_sr, int target_sr, int* up, int* down, int* taps_per_phase, int* n_pre_remove,
+                      int* filter_len);
+long long stx_resample_filter(int orig_sr, int target_sr, float* h_out, long long capacity);
+int stx_resample_poly(const float* d_in, const int64_t* d_in_offsets, const int32_t* d_in_lengths, int B, int orig_sr,
+                      int target_sr, float* d_out, const int64_t* d_out_offsets, const int32_t* d_out_lengths,
+                      int max_out_length, float* d_peaks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

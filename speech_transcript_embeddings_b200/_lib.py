@@ -43,6 +43,11 @@ _SIGNATURES = {
                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "stx_cosine_gather_sizes": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t),
                                           C.POINTER(C.c_size_t)]),
+    "stx_resample_plan": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "stx_resample_filter": (C.c_longlong, [C.c_int, C.c_int, C.c_void_p, C.c_longlong]),
+    "stx_resample_poly": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "stx_cosine_nxm_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]),

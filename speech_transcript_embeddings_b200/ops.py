@@ -59,6 +59,69 @@ def peak_abs(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor) ->
     return peak
 
 
+def resample_plan(orig_sr: int, target_sr: int) -> dict:
+    """up / down / taps per polyphase branch / leading outputs removed / padded filter length of the resampler."""
+    lib = _lib.load()
+    v = [C.c_int(0) for _ in range(5)]
+    _lib.check(lib.stx_resample_plan(int(orig_sr), int(target_sr), *[C.byref(x) for x in v]), "stx_resample_plan")
+    return dict(zip(("up", "down", "taps_per_phase", "n_pre_remove", "filter_len"), (x.value for x in v)))
+
+
+def resample_filter(orig_sr: int, target_sr: int) -> np.ndarray:
+    """The padded float32 low-pass the resampler applies (what scipy.signal.resample_poly hands to upfirdn)."""
+    lib = _lib.load()
+    n = resample_plan(orig_sr, target_sr)["filter_len"]
+    out = np.empty(n, np.float32)
+    got = lib.stx_resample_filter(int(orig_sr), int(target_sr), out.ctypes.data_as(C.c_void_p), n)
+    if got != n:
+        _lib.check(int(got) if got < 0 else -1, "stx_resample_filter")
+    return out
+
+
+def resample_out_lengths(lengths: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
+    """ceil(n * target_sr / orig_sr) per clip (librosa.resample's fix_length target), int32."""
+    g = int(np.gcd(int(orig_sr), int(target_sr)))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    return ((np.asarray(lengths, np.int64) * up + down - 1) // down).astype(np.int32)
+
+
+def resample_poly(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, lengths_host: np.ndarray,
+                  orig_sr: int, target_sr: int, want_peak: bool = True, align: int = 32):
+    """Device-side librosa.resample(..., res_type="polyphase") of packed clips (R/processor.py:82-86).
+
+    ``lengths_host`` is the host copy of ``lengths`` (the output layout is computed on the host).  Returns
+    (pcm_out float32 [total], offsets_out int64 [B] CUDA, lengths_out int32 [B] CUDA, lengths_out_host int32 [B],
+    peak float32 [B] = max(1, max|y|) or None); output clips start on ``align``-float boundaries.
+    """
+    lib = _lib.load()
+    _require_cuda(pcm, "pcm", torch.float32)
+    _require_cuda(offsets, "offsets", torch.int64)
+    _require_cuda(lengths, "lengths", torch.int32)
+    B = lengths.numel()
+    dev = pcm.device
+    out_len = resample_out_lengths(lengths_host, orig_sr, target_sr)
+    padded = (out_len.astype(np.int64) + (align - 1)) // align * align
+    out_off = np.zeros(B, np.int64)
+    if B > 1:
+        np.cumsum(padded[:-1], out=out_off[1:])
+    total = int(padded.sum())
+    meta = torch.empty(2 * B, dtype=torch.int64, pin_memory=True)
+    mv = meta.numpy()
+    mv[:B] = out_off
+    mv[B:].view(np.int32)[:B] = out_len
+    meta_d = meta.to(dev, non_blocking=True)
+    off_d = meta_d[:B]
+    len_d = meta_d[B:].view(torch.int32)[:B]
+    out = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+    peak = torch.empty(B, dtype=torch.float32, device=dev) if want_peak else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_resample_poly(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, int(orig_sr),
+                                         int(target_sr), out.data_ptr(), off_d.data_ptr(), len_d.data_ptr(),
+                                         int(out_len.max()) if B else 0, peak.data_ptr() if peak is not None else None,
+                                         _stream_ptr(dev)), "stx_resample_poly")
+    return out, off_d, len_d, out_len, peak
+
+
 def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_length: int, T_pad: int,
             padding_value: float = 0.0, normalize: bool = True, peak: torch.Tensor | None = None,
             want_mask: bool = True, out: torch.Tensor | None = None, mask: torch.Tensor | None = None):

@@ -8,9 +8,15 @@ Same constructor arguments, same method names, same return dictionaries:
   compute_similarity(e1, e2)                -> np.ndarray float32 [N]
 
 The float32 cast, the peak-normalise (R/processor.py:91-92) and the trim to ``max_audio_length``
-(:95-97) are kept; the feature extraction and the scoring run in libstx_b200.so.  Tokenisation, audio
-decoding and resampling are outside the hot path: they are delegated to the same third-party packages
-the reference uses and raise a clear error when those are not installed.
+(:95-97) are kept; the feature extraction and the scoring run in libstx_b200.so.  Tokenisation and audio
+decoding are outside the hot path: they are delegated to the same third-party packages the reference uses and
+raise a clear error when those are not installed.
+
+Resampling (R/processor.py:82-86) runs on the device as well (``resample="device"``, the default): the polyphase
+resampler of ``librosa.resample(..., res_type="polyphase")`` (= ``scipy.signal.resample_poly``), with the per-clip
+peak reduced in the same pass.  The reference's own default ``res_type`` is ``"soxr_hq"``, whose arithmetic lives in
+the soxr C library and cannot be reproduced bit for bit; ``resample="librosa"`` keeps the reference's exact host call
+(needs librosa) for users who want that filter.
 """
 from __future__ import annotations
 
@@ -44,7 +50,11 @@ class AudioTextProcessor:
 
     def __init__(self, text_model_name="sentence-transformers/all-roberta-large-v1",
                  audio_model_name="facebook/w2v-bert-2.0", device=None, max_text_length=256,
-                 sampling_rate=16000, max_audio_length=480000, tokenizer=None, padding_value=0.0):
+                 sampling_rate=16000, max_audio_length=480000, tokenizer=None, padding_value=0.0,
+                 resample="device"):
+        if resample not in ("device", "librosa"):
+            raise ValueError("resample must be 'device' (polyphase, on the GPU) or 'librosa' (the reference's host call)")
+        self.resample = resample
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda" if torch.cuda.is_available() else "cpu")
         self.max_text_length = max_text_length
@@ -85,11 +95,13 @@ class AudioTextProcessor:
         return self.process_audio_array(audio_array, orig_sr)
 
     def _prepare(self, audio_array, orig_sr):
-        if orig_sr != self.sampling_rate:
+        """Host side of R/processor.py:82-89: (optional host resampling,) float32 cast, 1-D."""
+        if orig_sr != self.sampling_rate and self.resample == "librosa":
             try:
                 import librosa
             except ImportError as e:
-                raise ImportError(f"resampling {orig_sr} Hz -> {self.sampling_rate} Hz needs librosa, as in the reference") from e
+                raise ImportError(f"resample='librosa': resampling {orig_sr} Hz -> {self.sampling_rate} Hz on the host "
+                                  "needs librosa, as in the reference (the default resample='device' does not)") from e
             audio_array = librosa.resample(np.asarray(audio_array), orig_sr=orig_sr, target_sr=self.sampling_rate)
         # NB the reference takes the peak over the untrimmed clip (R/processor.py:91-97); so do we:
         # the trim happens on the device through the per-clip lengths
@@ -99,14 +111,20 @@ class AudioTextProcessor:
         return self.process_audio_batch([audio_array], orig_sr)
 
     def process_audio_batch(self, audio_arrays, orig_sr):
-        """Batched form of process_audio_array (every clip gets its own peak-normalise and trim)."""
+        """Batched form of process_audio_array (every clip gets its own resampling, peak-normalise and trim)."""
         fe = self.feature_extractor
         full = [self._prepare(a, orig_sr) for a in audio_arrays]
-        # peak over the whole clip (before the trim), division fused into the kernel's load
         packed_full = fe.pack(full)
         pcm_d, off_d, len_d = fe.to_device(packed_full)
-        peak = ops.peak_abs(pcm_d, off_d, len_d)
-        lengths = np.minimum(packed_full.lengths, self.max_audio_length).astype(np.int32)
+        if orig_sr != self.sampling_rate and self.resample == "device":
+            # resample + per-clip peak in one pass over the original-rate PCM (R/processor.py:85, 91)
+            pcm_d, off_d, len_d, full_lengths, peak = ops.resample_poly(pcm_d, off_d, len_d, packed_full.lengths,
+                                                                        int(orig_sr), int(self.sampling_rate))
+        else:
+            # peak over the whole clip (before the trim), division fused into the kernel's load
+            full_lengths = packed_full.lengths
+            peak = ops.peak_abs(pcm_d, off_d, len_d)
+        lengths = np.minimum(full_lengths, self.max_audio_length).astype(np.int32)
         len_trim = torch.from_numpy(lengths).to(pcm_d.device, non_blocking=True)
         max_len = int(lengths.max()) if lengths.size else 0
         if self._recipe_k:

@@ -7,6 +7,7 @@ from conftest import load_golden
 from oracle import cosine as OC
 from oracle import fbank_k as OK
 from oracle import logmel_w as OW
+from oracle import resample as OR
 from speech_transcript_embeddings_b200 import synth
 
 
@@ -120,3 +121,35 @@ def test_pos_neg_oracle_matches_the_references_torch_ops():
         assert np.abs(ref["s_pos"] - s_pos.numpy()).max() < 1e-14 and np.abs(ref["per_sample"] - per.numpy()).max() < 1e-12
         assert abs(ref["loss"] - float(loss)) < 1e-12
         assert np.abs(ref["hr_neg"] - torch.sigmoid(s_neg / 0.1).numpy()).max() < 1e-14
+
+
+def test_resample_oracle_matches_golden_and_scipy_live():
+    """oracle/resample.py vs the scipy.signal.resample_poly fixtures (what librosa's res_type="polyphase" runs) and, when
+    scipy is importable, vs scipy itself on fresh clips; float32 summation noise only."""
+    g = load_golden("resample.npz")
+    for i, ((sr, n, seed), kind) in enumerate(zip(g["spec"], g["kinds"])):
+        x = synth.clip(str(kind), int(n), int(seed))
+        y = OR.resample_poly(x, int(sr), 16000)
+        ref = g[f"y_{i}"]
+        assert y.shape == ref.shape == (int(np.ceil(int(n) * 16000 / int(sr))),)
+        if ref.size:
+            assert np.abs(y - ref).max() <= 1e-6 * max(1.0, float(np.abs(x).max()))
+    ss = pytest.importorskip("scipy.signal")
+    for sr in (48000, 44100, 8000):
+        x = synth.clip("U", 5000, sr)
+        up, down = OR.plan(sr, 16000)
+        assert np.abs(OR.resample_poly(x, sr, 16000) - ss.resample_poly(x, up, down)).max() <= 1e-6
+        h_pad, _ = OR.design(up, down)
+        mr = max(up, down)
+        h = ss.firwin(20 * mr + 1, 1.0 / mr, window=("kaiser", 5.0)).astype(np.float32) * np.float32(up)
+        assert np.array_equal(h_pad[-h.size:], h) and not h_pad[:-h.size].any()
+
+
+def test_library_resample_filter_matches_oracle(lib):
+    from speech_transcript_embeddings_b200 import ops
+    for sr in (48000, 44100, 32000, 22050, 8000, 24000, 11025, 96000):
+        p = ops.resample_plan(sr, 16000)
+        h_pad, npr = OR.design(p["up"], p["down"])
+        assert (p["up"], p["down"]) == OR.plan(sr, 16000) and p["n_pre_remove"] == npr and p["filter_len"] == h_pad.size
+        assert np.abs(ops.resample_filter(sr, 16000) - h_pad).max() <= 1e-9      # at most a last-bit difference
+    assert list(ops.resample_out_lengths(np.array([0, 1, 3, 48000, 48001]), 48000, 16000)) == [0, 1, 1, 16000, 16001]
