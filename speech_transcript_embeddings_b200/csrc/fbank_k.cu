@@ -45,6 +45,7 @@
 #include "codelets.cuh"
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <mutex>
 
 namespace stx {
@@ -454,6 +455,368 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     }
 }
 
+// =================================================================================================================
+// k_frames_duo: the same arithmetic as k_frames, organised as TWO INDEPENDENT HALF-CTAs of 8 warps, each on its own
+// 32-frame tile, so that one group's shared-memory phases overlap the other's FP64 phases (in k_frames all 16 warps move
+// through the phases together: FP64 pipe 35 % busy + LSU pipe 48 % busy, never at the same time; a synthetic FFT core,
+// tools/microbench_overlap.cu, runs 1.6 x faster with two staggered groups).
+//
+// Two tiles in flight need two exchange buffers, and a 32-frame float64 exchange is 128 KB.  Each group therefore exchanges
+// in TWO HALVES through a 64 KB buffer: pass 1 (two roles per warp) stores the twiddled rows k1 = 0..7 and 16 and STASHES
+// rows 8..15 in tensor memory (tcgen05.st: a warp's own 32 TMEM lanes, 32 columns per role -- TMEM is used as a private
+// 256 KB register file extension here, no MMA involved); after pass 2 has read the first half, the stash comes back
+// (tcgen05.ld) into the same buffer for the second half.  Between a tile's last exchange load and the next tile's first
+// store the buffer doubles as the TMA landing zone of the next tile's PCM and as the staging area of the log-mel rows.
+//
+// Group-private barriers (bar.sync 1 + g, 256).  Per tile: d ready | H1 stored | H1 loaded | H2 stored | P complete | rows staged.
+// Measured on cfg2: 224 us against 244 us for k_frames (FP64 pipe 39 %, LSU 53 %: the two groups drift apart on their own;
+// delaying group 1 by a fraction of the tile period only adds the delay).  STX_K_SINGLE=1 selects k_frames for A/B runs.
+constexpr int kGWarps = 8;
+constexpr int kGThreads = kGWarps * 32;          // 256
+constexpr int kGStat = 3 * kMel;                 // 240 threads of a group store 3 rows of 80 bins per step
+constexpr int kStageBytes = kStage * 4;          // 21 472
+constexpr int kOutStageOff = 24576;              // byte offset of the staged log-mel rows inside the exchange buffer
+static_assert(kStageBytes <= kOutStageOff && kOutStageOff + kTile * kOutRow * 4 <= 65536, "landing zone and staged rows share the exchange buffer");
+
+struct SmemG {
+    double2 ex[8][16][kTile];    // one HALF of the exchange: [slot][n2][lane].  H1: slot 0 = (row 0, row 16) (both real), slots
+                                 // 1..7 = rows 1..7;  H2: slot s = row 8 + s
+    union {
+        double d[kDBuf];
+        float  P[256][kTile];
+    } u;
+    double  psum[kTile][17];
+    double  cval[kTile];
+    double  xb[kTile];
+    unsigned long long mbar;     // TMA completion
+    unsigned long long cbar;     // cval ready (one arrival per warp of the group)
+};
+struct SmemDuo {
+    SmemG g[2];
+    float melw[kMelWeights];
+    int   melfirst[kMel];
+    unsigned tmem_base;
+};
+static_assert(sizeof(SmemDuo) <= 227 * 1024, "one CTA per SM must fit in 227 KB");
+constexpr unsigned kTmemCols = 256;              // 4 warps per TMEM lane quarter x 2 roles x 32 columns
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGThreads) : "memory"); }
+
+// 16 doubles <-> 32 TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const double (&v)[16]) {
+    unsigned r[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { r[2 * i] = (unsigned)__double2loint(v[i]); r[2 * i + 1] = (unsigned)__double2hiint(v[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[16]) {
+    unsigned r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+
+template <bool kPeak>
+__global__ void __launch_bounds__(kThreads, 1)
+k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
+             const float* __restrict__ peaks, const KTables* __restrict__ tab, int T_pad, int chunk_frames,
+             int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemDuo& sm = *reinterpret_cast<SmemDuo*>(smem_raw);
+
+    const int b = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const int n = lengths[b];
+    const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+    const int t_begin = chunk * chunk_frames;
+    if (t_begin >= T) return;                       // uniform per CTA (before the TMEM allocation)
+    const int t_end = min(T, t_begin + chunk_frames);
+    const float* clip = pcm + offsets[b];
+    const bool aligned = (reinterpret_cast<unsigned long long>(clip) & 15ull) == 0;
+    const float peak = kPeak ? peaks[b] : 1.0f;
+    float* out_b = out + (size_t)b * T_pad * kMel;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = warp >> 3;                        // group
+    const int w8 = warp & 7;                        // warp within the group: roles w8 and w8 + 8, row tasks w8 and 8 + w8
+    const int tl = tid & (kGThreads - 1);           // thread within the group
+    SmemG& sg = sm.g[g];
+    float* stage = reinterpret_cast<float*>(&sg.ex[0][0][0]);                         // TMA landing zone (between tiles)
+    float* outstage = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&sg.ex[0][0][0]) + kOutStageOff);
+    const int t_first = t_begin + g * kTile;        // this group's tiles: t_first, t_first + 64, ...
+    constexpr int kStep = 2 * kTile;
+
+    auto prefetch = [&](const int tn) {             // PCM of the group's tile at frame tn -> the (idle) exchange buffer
+        if (tl == 0 && tn < t_end) {
+            const int sn = tn * kHop;
+            const StageRange nx = stage_range(sn, n, aligned);
+            if (nx.hi > nx.lo) {
+                mbar_expect_tx(&sg.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
+                bulk_g2s(stage + (nx.lo - (sn - kLead)), clip + nx.lo, (unsigned)(nx.hi - nx.lo) * 4u, &sg.mbar);
+            }
+        }
+    };
+    if (tl == 0) {
+        mbar_init(&sg.mbar, 1);
+        mbar_init(&sg.cbar, kGWarps);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
+    if (tid < kMel) sm.melfirst[tid] = tab->melfirst[tid];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                // mbarrier init, tables, TMEM base visible
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    prefetch(t_first);
+    // this thread's stash: TMEM lanes of the warp's quarter, 32 columns per role
+    const unsigned tstash = sm.tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * 64);
+
+    unsigned long long s1 = 0, s2h = 0, s2l = 0;    // fixed-point statistics of bin tl % 80 over the rows tl / 80 + 3 i
+    const int sbin = tl % kMel, srow = tl / kMel;
+    unsigned parity = 0, cparity = 0;
+
+    // convert(tc): landed PCM of the tile at frame tc -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161
+    auto convert = [&](const int tc) {
+        const int s0 = tc * kHop;
+        const StageRange sr = stage_range(s0, n, aligned);
+        if (sr.hi > sr.lo) { mbar_wait(&sg.mbar, parity); parity ^= 1; }
+        auto sample = [&](int gi) -> float {        // x[gi] of this clip, 0 outside
+            float v = 0.0f;
+            if (gi >= sr.lo && gi < sr.hi) v = stage[gi - s0 + kLead];
+            else if (gi >= 0 && gi < n) v = __ldg(clip + gi);
+            if (kPeak) v = v / peak;                  // float32 division, like numpy's (R/processor.py:92)
+            return v;
+        };
+        if (sr.lo == s0 - kLead && sr.hi == s0 + kTileSamples + 4) {
+            // whole tile landed and inside the clip.  240 threads, thread (u, c) = (tl / 80, tl % 80) converts the half rows
+            // u + 3 j (67 half rows of 80 samples): no division in the loop, independent iterations
+            if (tl < kGStat) {
+                const int u = tl / 80, c = tl - u * 80;
+#pragma unroll
+                for (int j = 0; j < 23; ++j) {
+                    const int hr = u + 3 * j;
+                    if (hr < 67) {
+                        const float* src = stage + kLead + 80 * hr + c;
+                        float xm = src[-1], xi = src[0];
+                        if (kPeak) { xm = xm / peak; xi = xi / peak; }
+                        sg.u.d[80 * hr + c + (hr >> 1)] = fma(-0.97, (double)xm, (double)xi);
+                    }
+                }
+            }
+            if (tl < kTile) {
+                float xa = stage[kLead + tl * kHop + kFrame - 1], xz = stage[kLead - 1 + tl * kHop];
+                if (kPeak) { xa = xa / peak; xz = xz / peak; }
+                sg.xb[tl] = 0.97 * ((double)xa - (double)xz);
+            }
+        } else {
+#pragma unroll 1
+            for (int i = tl; i < kTileSamples; i += kGThreads)
+                sg.u.d[i + (unsigned)i / kHop] = fma(-0.97, (double)sample(s0 + i - 1), (double)sample(s0 + i));
+            if (tl < kTile)
+                sg.xb[tl] = 0.97 * ((double)sample(s0 + tl * kHop + kFrame - 1) - (double)sample(s0 + tl * kHop - 1));
+        }
+    };
+
+    // the first trip (t0 = t_first - kStep) only converts the group's first tile: ONE copy of every phase in the code
+    for (int t0 = t_first - kStep; t0 < t_end; t0 += kStep) {
+      if (t0 >= t_first) {
+        // ---- window + pass 1, two roles per warp: rows 0..7 and 16 -> exchange (H1), rows 8..15 -> TMEM stash ----
+        auto pass1 = [&](const int role, const int which) {
+            const double* D = sg.u.d + kDRow * lane + role;
+            double y[25];
+            double sa = 0.0, sb = 0.0;
+            constexpr int kOrder1[25] = {0, 16, 8, 24, 4, 20, 12, 1, 17, 9, 5, 21, 13, 2, 18, 10, 6, 22, 14, 3, 19, 11, 7, 23, 15};
+            double v1[25];
+#pragma unroll
+            for (int j = 0; j < 25; ++j) {
+                const int n1 = kOrder1[j];
+                v1[n1] = lds_f64(D + 16 * n1 + (n1 >= 10) + (n1 >= 20));
+            }
+#pragma unroll
+            for (int n1 = 0; n1 < 25; ++n1) {
+                y[n1] = c_win[role][n1] * v1[n1];
+                if (n1 & 1) sb += v1[n1]; else sa += v1[n1];
+            }
+            sg.psum[lane][role] = sa + sb;
+            double re[17], im[17];
+            codelets::k_pass1<double>(y, re, im);
+            sg.ex[0][role][lane] = make_double2(re[0], re[16]);
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) {
+                const double2 t = *reinterpret_cast<const double2*>(&c_tw[role][k1]);
+                sg.ex[k1][role][lane] = make_double2(fma(re[k1], t.x, -(im[k1] * t.y)), fma(re[k1], t.y, im[k1] * t.x));
+            }
+            double hs[16];
+#pragma unroll
+            for (int k1 = 8; k1 < 16; ++k1) {
+                const double2 t = *reinterpret_cast<const double2*>(&c_tw[role][k1]);
+                hs[2 * (k1 - 8)] = fma(re[k1], t.x, -(im[k1] * t.y));
+                hs[2 * (k1 - 8) + 1] = fma(re[k1], t.y, im[k1] * t.x);
+            }
+            tmem_st16(tstash + (unsigned)(which * 32), hs);
+        };
+        pass1(w8, 0);
+        pass1(w8 + kGWarps, 1);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        group_bar(g);                               // H1 complete, psum complete; d is dead, its storage becomes the power spectrum
+
+        // ---- c = 0.03 * mean(frame): warp w8 sums the 16 partials of frames 4 w8 .. 4 w8 + 3 ----
+        {
+            const int fr = 4 * w8 + (lane >> 3), r = lane & 7;
+            double v = sg.psum[fr][r] + sg.psum[fr][r + 8];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (r == 0) sg.cval[fr] = (v - sg.xb[fr]) * (1.0 / 400.0);
+            if (w8 == 1) sg.u.P[0][lane] = 0.0f;     // padded mel filters may touch bin 0 with a zero weight
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sg.cbar)) : "memory");
+        }
+
+        // ---- pass 2, first half: row task w8 (task 0 = the two real rows 0 and 16, task k = row k) ----
+        double xr[16], xi[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const double2 v = lds_v2f64(&sg.ex[w8][n2][lane]);
+            xr[n2] = v.x; xi[n2] = v.y;
+        }
+        group_bar(g);                               // H1 is in registers: the exchange buffer is free for H2
+        // ---- the stash comes back: rows 8..15 of both roles -> exchange (H2) ----
+        {
+            double hs[16];
+            tmem_ld16(tstash, hs);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) sg.ex[s][w8][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
+            tmem_ld16(tstash + 32u, hs);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) sg.ex[s][w8 + kGWarps][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
+        }
+        group_bar(g);                               // H2 complete
+
+        double c = 0.0;
+        auto put = [&](int bin, double pr, double pi, double2 wh) {
+            const double a = fma(-c, wh.x, pr), bb = fma(-c, wh.y, pi);
+            sg.u.P[bin][lane] = power_to_f32(fma(a, a, bb * bb));
+        };
+        if (w8 == 0) {
+            double e0r[7], e0i[7], e16r[8], e16i[8];
+            codelets::k_pass2_edge<double>(xr, xi, e0r, e0i, e16r, e16i);
+            mbar_wait(&sg.cbar, cparity);
+            c = sg.cval[lane];
+#pragma unroll
+            for (int k2 = 1; k2 < 8; ++k2) put(32 * k2, e0r[k2 - 1], e0i[k2 - 1], c_wh[0][k2]);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) put(16 + 32 * k2, e16r[k2], e16i[k2], c_wh[0][8 + k2]);
+        } else {
+            double yr[16], yi[16];
+            codelets::dft16<double>(xr, xi, yr, yi);
+            mbar_wait(&sg.cbar, cparity);
+            c = sg.cval[lane];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2)
+                put(k2 < 8 ? w8 + 32 * k2 : 512 - w8 - 32 * k2, yr[k2], yi[k2], c_wh[w8][k2]);
+        }
+        cparity ^= 1;
+        // ---- pass 2, second half: row 8 + w8 ----
+        {
+            const int row = kGWarps + w8;
+            constexpr int kOrder2[16] = {0, 8, 4, 12, 1, 9, 5, 13, 2, 10, 6, 14, 3, 11, 7, 15};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n2 = kOrder2[j];
+                const double2 v = lds_v2f64(&sg.ex[w8][n2][lane]);
+                xr[n2] = v.x; xi[n2] = v.y;
+            }
+            double yr[16], yi[16];
+            codelets::dft16<double>(xr, xi, yr, yi);
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2)
+                put(k2 < 8 ? row + 32 * k2 : 512 - row - 32 * k2, yr[k2], yi[k2], c_wh[row][k2]);
+        }
+        group_bar(g);                               // power spectrum complete; the exchange buffer is idle until the next pass 1
+        prefetch(t0 + kStep);                       // ... and takes the next tile's PCM meanwhile
+
+        // ---- sparse mel + ln: warp w8 owns the mel bins of roles w8 and w8 + 8 ----
+        {
+            const float* Pl = &sg.u.P[0][lane];
+            float* orow = outstage + lane * kOutRow;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int wr = w8 + h * kGWarps;
+                orow[wr]      = mel_slot<0>(Pl, sm.melw, sm.melfirst, wr);
+                orow[wr + 16] = mel_slot<1>(Pl, sm.melw, sm.melfirst, wr);
+                orow[wr + 32] = mel_slot<2>(Pl, sm.melw, sm.melfirst, wr);
+                orow[wr + 48] = mel_slot<3>(Pl, sm.melw, sm.melfirst, wr);
+                orow[wr + 64] = mel_slot<4>(Pl, sm.melw, sm.melfirst, wr);
+            }
+        }
+        group_bar(g);
+
+        // ---- coalesced store of the tile's rows + statistics ----
+        if (tl < kGStat) {
+            const int rows = min(t_end - t0, kTile);
+            const int keep = min(T_pad - t0, rows);           // frames >= T_pad count for the statistics but are not stored
+            float* dst = out_b + (size_t)t0 * kMel + tl;
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+                const int row = srow + 3 * i;
+                if (row < rows) {
+                    const float v = outstage[row * kOutRow + sbin];
+                    if (row < keep) dst[i * kGStat] = v;
+                    const double vd = (double)v;
+                    const double sq = vd * vd, hi = sq + kFixH, lo = sq - (hi - kFixH);      // all exact
+                    s1 += (unsigned long long)__double_as_longlong(vd + kFix1) - (unsigned long long)__double_as_longlong(kFix1);
+                    s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
+                    s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
+                }
+            }
+        }
+      }
+        if (t0 + kStep < t_end) convert(t0 + kStep);
+        group_bar(g);                               // d ready; landing zone and staged rows consumed
+    }
+
+    // ---- per-chunk statistics: ordered reduction over the 2 x 3 row groups ----
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(&sm.g[0].ex[0][0][0]);     // [3][6][80]
+    if (tl < kGStat) {
+        red[g * kGStat + tl] = s1;
+        red[kStatThreads + g * kGStat + tl] = s2h;
+        red[2 * kStatThreads + g * kGStat + tl] = s2l;
+    }
+    __syncthreads();
+    if (tid < kStatWords) {
+        const int which = tid / kMel, m = tid - which * kMel;
+        unsigned long long acc = 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc += red[which * kStatThreads + q * kMel + m];
+        partials[((size_t)b * chunks_per_clip + chunk) * kStatWords + tid] = (long long)acc;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // in-place CMVN + padding rows + mask.  One thread per float4 of a clip's [T_pad, 80] block.
 //   rows t < T            normalised features
 //   rows T <= t < T2      padding_value (T2 = T rounded up to even: the half of the last stacked frame of an odd clip)
@@ -614,6 +977,8 @@ int get_tables(const KTables** out) {
         STX_CUDA(cudaMemcpy(d, &h, sizeof(KTables), cudaMemcpyHostToDevice));
         STX_CUDA(cudaFuncSetAttribute(k_frames<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         STX_CUDA(cudaFuncSetAttribute(k_frames<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        STX_CUDA(cudaFuncSetAttribute(k_frames_duo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDuo)));
+        STX_CUDA(cudaFuncSetAttribute(k_frames_duo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDuo)));
         g_tab[dev] = d;
     }
     *out = g_tab[dev];
@@ -634,6 +999,21 @@ inline int pick_chunk(int B, int max_frames, int sms) {
         if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = chunk; }
     }
     return best;
+}
+// k_frames_duo: a CTA works on two tiles at a time, so chunks are multiples of 64 frames and cost ceil(tiles / 2) rounds
+inline int pick_chunk_duo(int B, int max_frames, int sms) {
+    int best = kMinChunk;
+    long long best_cost = -1;
+    for (int chunk = kMinChunk; chunk <= 512; chunk += 2 * kTile) {
+        const long long ctas = (long long)B * ((max_frames + chunk - 1) / chunk);
+        const long long cost = ((ctas + sms - 1) / sms) * (chunk / (2 * kTile));
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = chunk; }
+    }
+    return best;
+}
+inline bool use_duo() {
+    static const bool v = [] { const char* e = std::getenv("STX_K_SINGLE"); return !(e && e[0] == '1'); }();
+    return v;
 }
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
@@ -673,11 +1053,20 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
         STX_CUDA(cudaGetDevice(&dev));
         STX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int chunk_frames = pick_chunk(B, max_frames, sms);
+    const bool duo = use_duo();
+    const int chunk_frames = duo ? pick_chunk_duo(B, max_frames, sms) : pick_chunk(B, max_frames, sms);
     const int chunks = std::max((max_frames + chunk_frames - 1) / chunk_frames, 1);
     long long* partials = static_cast<long long*>(d_ws);
     if (frames_of(max_length) > 0) {
-        if (d_peak) {
+        if (duo && d_peak) {
+            STX_LAUNCH(k_frames_duo<true>, dim3(chunks, B), dim3(kThreads), sizeof(SmemDuo), st,
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
+                       chunk_frames, chunks, d_out, partials);
+        } else if (duo) {
+            STX_LAUNCH(k_frames_duo<false>, dim3(chunks, B), dim3(kThreads), sizeof(SmemDuo), st,
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
+                       chunk_frames, chunks, d_out, partials);
+        } else if (d_peak) {
             STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
                        d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
                        chunk_frames, chunks, d_out, partials);
