@@ -323,6 +323,8 @@ def run_b200(args):
     per_kernel = {}
     for name, kms in recs:
         per_kernel.setdefault(name, []).append(kms)
+    if dominant not in per_kernel:                         # recipe K: k_frames_duo<false> (default) or k_frames<false> (STX_K_SINGLE=1)
+        dominant = max((k for k in per_kernel if k.startswith(dominant.split("<")[0])), key=lambda k: sum(per_kernel[k]))
     dom_ms = statistics.mean(per_kernel[dominant])
     step_ms_prof = sum(sum(v) for v in per_kernel.values()) / args.steps
     peak, peak_src = measured_hbm_peak()
