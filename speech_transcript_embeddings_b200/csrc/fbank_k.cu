@@ -476,8 +476,17 @@ constexpr int kGThreads = kGWarps * 32;          // 256
 constexpr int kGStat = 3 * kMel;                 // 240 threads of a group store 3 rows of 80 bins per step
 constexpr int kStageBytes = kStage * 4;          // 21 472
 constexpr int kOutStageOff = 24576;              // byte offset of the staged log-mel rows inside the exchange buffer
+constexpr int kRedOff = 40960;                   // byte offset of the per-item statistics reduction inside the exchange buffer
 static_assert(kStageBytes <= kOutStageOff && kOutStageOff + kTile * kOutRow * 4 <= 65536, "landing zone and staged rows share the exchange buffer");
 
+// One 32-frame tile of a work item (clip b, chunk): everything the phases need, kept in SHARED memory and read where it is
+// used, so that no per-tile state is live in registers across the FFT phases
+struct TileDesc {
+    const float* clip; float* out_b; long long* part;
+    int n, t0, t_end, item;
+    float peak;
+    int aligned, valid, last;    // last: the item ends with this tile (flush the statistics)
+};
 struct SmemG {
     double2 ex[8][16][kTile];    // one HALF of the exchange: [slot][n2][lane].  H1: slot 0 = (row 0, row 16) (both real), slots
                                  // 1..7 = rows 1..7;  H2: slot s = row 8 + s
@@ -490,6 +499,7 @@ struct SmemG {
     double  xb[kTile];
     unsigned long long mbar;     // TMA completion
     unsigned long long cbar;     // cval ready (one arrival per warp of the group)
+    TileDesc desc[2];            // the tile in flight and the next one (written by the group's thread 0)
 };
 struct SmemDuo {
     SmemG g[2];
@@ -533,22 +543,10 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[16]) {
 template <bool kPeak>
 __global__ void __launch_bounds__(kThreads, 1)
 k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
-             const float* __restrict__ peaks, const KTables* __restrict__ tab, int T_pad, int chunk_frames,
+             const float* __restrict__ peaks, const KTables* __restrict__ tab, int B, int T_pad, int chunk_frames,
              int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemDuo& sm = *reinterpret_cast<SmemDuo*>(smem_raw);
-
-    const int b = blockIdx.y;
-    const int chunk = blockIdx.x;
-    const int n = lengths[b];
-    const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
-    const int t_begin = chunk * chunk_frames;
-    if (t_begin >= T) return;                       // uniform per CTA (before the TMEM allocation)
-    const int t_end = min(T, t_begin + chunk_frames);
-    const float* clip = pcm + offsets[b];
-    const bool aligned = (reinterpret_cast<unsigned long long>(clip) & 15ull) == 0;
-    const float peak = kPeak ? peaks[b] : 1.0f;
-    float* out_b = out + (size_t)b * T_pad * kMel;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -559,16 +557,46 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     SmemG& sg = sm.g[g];
     float* stage = reinterpret_cast<float*>(&sg.ex[0][0][0]);                         // TMA landing zone (between tiles)
     float* outstage = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(&sg.ex[0][0][0]) + kOutStageOff);
-    const int t_first = t_begin + g * kTile;        // this group's tiles: t_first, t_first + 64, ...
-    constexpr int kStep = 2 * kTile;
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(&sg.ex[0][0][0]) + kRedOff);
 
-    auto prefetch = [&](const int tn) {             // PCM of the group's tile at frame tn -> the (idle) exchange buffer
-        if (tl == 0 && tn < t_end) {
-            const int sn = tn * kHop;
-            const StageRange nx = stage_range(sn, n, aligned);
+    // PERSISTENT: the grid is one CTA per SM and every GROUP streams through its own list of work items, item =
+    // (clip b, chunk of chunk_frames frames), items G, G + groups, G + 2 groups, ... with G = 2 blockIdx.x + g.  The TMEM
+    // allocation, the tables and the pipeline fill are paid once per kernel instead of once per chunk (2.3 us each, 7 % of
+    // the non-persistent form), and the groups never meet again after the first barrier, so they drift into complementary
+    // phases on their own.
+    const int items = B * chunks_per_clip;
+    const int item_step = 2 * gridDim.x;
+    // (thread 0 of the group only) first tile of the first non-empty item at or after `item` in this group's list
+    auto open_item = [&](int item, TileDesc& d) {
+        d.valid = 0; d.last = 0; d.item = item;
+        for (; item < items; item += item_step) {
+            const int b = item / chunks_per_clip, chunk = item - b * chunks_per_clip;
+            const int n = __ldg(lengths + b);
+            const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+            const int t_begin = chunk * chunk_frames;
+            if (t_begin >= T) continue;
+            d.valid = 1; d.item = item; d.n = n; d.t0 = t_begin; d.t_end = min(T, t_begin + chunk_frames);
+            d.clip = pcm + __ldg(offsets + b);
+            d.aligned = (reinterpret_cast<unsigned long long>(d.clip) & 15ull) == 0;
+            d.peak = kPeak ? __ldg(peaks + b) : 1.0f;
+            d.out_b = out + (size_t)b * T_pad * kMel;
+            d.part = partials + (size_t)item * kStatWords;
+            break;
+        }
+    };
+    // (thread 0 of the group only) d = the tile after c; marks c as the last tile of its item when the item changes
+    auto next_tile = [&](TileDesc& c, TileDesc& d) {
+        if (c.t0 + kTile < c.t_end) { d = c; d.t0 += kTile; c.last = 0; }
+        else { open_item(c.item + item_step, d); c.last = 1; }
+    };
+
+    auto prefetch = [&](const TileDesc& d) {        // (thread 0 of the group) PCM of the tile -> the (idle) exchange buffer
+        if (d.valid) {
+            const int sn = d.t0 * kHop;
+            const StageRange nx = stage_range(sn, d.n, d.aligned);
             if (nx.hi > nx.lo) {
                 mbar_expect_tx(&sg.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
-                bulk_g2s(stage + (nx.lo - (sn - kLead)), clip + nx.lo, (unsigned)(nx.hi - nx.lo) * 4u, &sg.mbar);
+                bulk_g2s(stage + (nx.lo - (sn - kLead)), d.clip + nx.lo, (unsigned)(nx.hi - nx.lo) * 4u, &sg.mbar);
             }
         }
     };
@@ -585,7 +613,11 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                // mbarrier init, tables, TMEM base visible
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    prefetch(t_first);
+    if (tl == 0) {
+        open_item(2 * blockIdx.x + g, sg.desc[0]);
+        prefetch(sg.desc[0]);
+    }
+    group_bar(g);                                   // the first descriptor is visible
     // this thread's stash: TMEM lanes of the warp's quarter, 32 columns per role
     const unsigned tstash = sm.tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((warp >> 2) * 64);
 
@@ -593,9 +625,13 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     const int sbin = tl % kMel, srow = tl / kMel;
     unsigned parity = 0, cparity = 0;
 
-    // convert(tc): landed PCM of the tile at frame tc -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161
-    auto convert = [&](const int tc) {
-        const int s0 = tc * kHop;
+    // convert(td): landed PCM of tile td -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161
+    auto convert = [&](const TileDesc& td) {
+        const int n = td.n;
+        const float* clip = td.clip;
+        const bool aligned = td.aligned != 0;
+        const float peak = td.peak;
+        const int s0 = td.t0 * kHop;
         const StageRange sr = stage_range(s0, n, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sg.mbar, parity); parity ^= 1; }
         auto sample = [&](int gi) -> float {        // x[gi] of this clip, 0 outside
@@ -635,9 +671,12 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         }
     };
 
-    // the first trip (t0 = t_first - kStep) only converts the group's first tile: ONE copy of every phase in the code
-    for (int t0 = t_first - kStep; t0 < t_end; t0 += kStep) {
-      if (t0 >= t_first) {
+    // the first trip only converts the group's first tile: ONE copy of every phase in the code
+    int slot = 0;
+    bool first_trip = true;
+    while (sg.desc[first_trip ? 0 : slot].valid) {
+      if (!first_trip) {
+        if (tl == 0) next_tile(sg.desc[slot], sg.desc[slot ^ 1]);      // visible to the group after the next barrier
         // ---- window + pass 1, two roles per warp: rows 0..7 and 16 -> exchange (H1), rows 8..15 -> TMEM stash ----
         auto pass1 = [&](const int role, const int which) {
             const double* D = sg.u.d + kDRow * lane + role;
@@ -752,7 +791,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 put(k2 < 8 ? row + 32 * k2 : 512 - row - 32 * k2, yr[k2], yi[k2], c_wh[row][k2]);
         }
         group_bar(g);                               // power spectrum complete; the exchange buffer is idle until the next pass 1
-        prefetch(t0 + kStep);                       // ... and takes the next tile's PCM meanwhile
+        if (tl == 0) prefetch(sg.desc[slot ^ 1]);   // ... and takes the next tile's PCM meanwhile
 
         // ---- sparse mel + ln: warp w8 owns the mel bins of roles w8 and w8 + 8 ----
         {
@@ -771,6 +810,9 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         group_bar(g);
 
         // ---- coalesced store of the tile's rows + statistics ----
+        const TileDesc& cur = sg.desc[slot];
+        const int t0 = cur.t0, t_end = cur.t_end;
+        float* const out_b = cur.out_b;
         if (tl < kGStat) {
             const int rows = min(t_end - t0, kTile);
             const int keep = min(T_pad - t0, rows);           // frames >= T_pad count for the statistics but are not stored
@@ -789,28 +831,25 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 }
             }
         }
+        if (cur.last) {
+            // ---- last tile of the item: the group's 3 row groups -> partials[item] (ordered, integer: exact) ----
+            if (tl < kGStat) { red[tl] = s1; red[kGStat + tl] = s2h; red[2 * kGStat + tl] = s2l; }
+            group_bar(g);
+            if (tl < kStatWords) {
+                const int which = tl / kMel, m = tl - which * kMel;
+                cur.part[tl] = (long long)(red[which * kGStat + m] + red[which * kGStat + kMel + m] + red[which * kGStat + 2 * kMel + m]);
+            }
+            s1 = 0; s2h = 0; s2l = 0;
+        }
+        slot ^= 1;
       }
-        if (t0 + kStep < t_end) convert(t0 + kStep);
+        if (sg.desc[slot].valid) convert(sg.desc[slot]);
         group_bar(g);                               // d ready; landing zone and staged rows consumed
+        first_trip = false;
     }
 
-    // ---- per-chunk statistics: ordered reduction over the 2 x 3 row groups ----
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    unsigned long long* red = reinterpret_cast<unsigned long long*>(&sm.g[0].ex[0][0][0]);     // [3][6][80]
-    if (tl < kGStat) {
-        red[g * kGStat + tl] = s1;
-        red[kStatThreads + g * kGStat + tl] = s2h;
-        red[2 * kStatThreads + g * kGStat + tl] = s2l;
-    }
-    __syncthreads();
-    if (tid < kStatWords) {
-        const int which = tid / kMel, m = tid - which * kMel;
-        unsigned long long acc = 0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) acc += red[which * kStatThreads + q * kMel + m];
-        partials[((size_t)b * chunks_per_clip + chunk) * kStatWords + tid] = (long long)acc;
-    }
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kTmemCols) : "memory");
@@ -1000,13 +1039,15 @@ inline int pick_chunk(int B, int max_frames, int sms) {
     }
     return best;
 }
-// k_frames_duo: a CTA works on two tiles at a time, so chunks are multiples of 64 frames and cost ceil(tiles / 2) rounds
+// k_frames_duo is persistent: 2 * sms groups stream through B * ceil(max_frames / chunk) items, so the chunk (>= kMinChunk
+// frames: the partials workspace is sized for that) minimises items-per-group * tiles-per-item; ties go to the larger chunk
 inline int pick_chunk_duo(int B, int max_frames, int sms) {
     int best = kMinChunk;
     long long best_cost = -1;
-    for (int chunk = kMinChunk; chunk <= 512; chunk += 2 * kTile) {
-        const long long ctas = (long long)B * ((max_frames + chunk - 1) / chunk);
-        const long long cost = ((ctas + sms - 1) / sms) * (chunk / (2 * kTile));
+    for (int chunk = kMinChunk; chunk <= 512; chunk += kTile) {
+        const long long items = (long long)B * ((max_frames + chunk - 1) / chunk);
+        const long long groups = 2 * std::max<long long>(1, std::min<long long>(sms, (items + 1) / 2));   // items = 0: clips shorter than a frame
+        const long long cost = ((items + groups - 1) / groups) * (chunk / kTile);
         if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = chunk; }
     }
     return best;
@@ -1054,17 +1095,22 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
         STX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const bool duo = use_duo();
-    const int chunk_frames = duo ? pick_chunk_duo(B, max_frames, sms) : pick_chunk(B, max_frames, sms);
+    int chunk_frames = duo ? pick_chunk_duo(B, max_frames, sms) : pick_chunk(B, max_frames, sms);
+    if (const char* e = std::getenv("STX_K_CHUNK")) {        // development: force the frames per work item (a multiple of 32, >= 64)
+        const int v = std::atoi(e);
+        if (v >= kMinChunk && v % kTile == 0) chunk_frames = v;
+    }
     const int chunks = std::max((max_frames + chunk_frames - 1) / chunk_frames, 1);
     long long* partials = static_cast<long long*>(d_ws);
     if (frames_of(max_length) > 0) {
+        const int duo_grid = (int)std::min<long long>(sms, ((long long)B * chunks + 1) / 2);
         if (duo && d_peak) {
-            STX_LAUNCH(k_frames_duo<true>, dim3(chunks, B), dim3(kThreads), sizeof(SmemDuo), st,
-                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
+            STX_LAUNCH(k_frames_duo<true>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, T_pad,
                        chunk_frames, chunks, d_out, partials);
         } else if (duo) {
-            STX_LAUNCH(k_frames_duo<false>, dim3(chunks, B), dim3(kThreads), sizeof(SmemDuo), st,
-                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,
+            STX_LAUNCH(k_frames_duo<false>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
+                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, T_pad,
                        chunk_frames, chunks, d_out, partials);
         } else if (d_peak) {
             STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,

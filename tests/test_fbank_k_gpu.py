@@ -259,3 +259,15 @@ def test_unaligned_clip_starts_take_the_plain_load_path(cuda_device):
     with np.errstate(all="ignore"):
         ref_x, ref_m = OK.extract(clips)
     assert np.abs(x0.numpy() - ref_x).max() <= TOL and np.array_equal(m0.numpy(), ref_m)
+
+
+def test_sub_batch_of_clips_shorter_than_a_frame(cuda_device):
+    """The chunked host pipeline can hand the kernel a sub-batch whose clips all have zero frames while T_pad (the whole
+    batch's) is positive: every row is padding, every mask entry 0 (found by tests/scripts/stress_parity.py: the persistent
+    kernel's work-item count was 0 and the chunk picker divided by it)."""
+    from speech_transcript_embeddings_b200 import ops
+    pcm = torch.zeros(512, dtype=torch.float32, device=cuda_device)
+    off = torch.tensor([0, 256], dtype=torch.int64, device=cuda_device)
+    lens = torch.tensor([100, 399], dtype=torch.int32, device=cuda_device)
+    x, m = ops.fbank_k(pcm, off, lens, 399, 6, padding_value=1.0)
+    assert x.shape == (2, 3, 160) and bool((x == 1.0).all()) and bool((m == 0).all())
