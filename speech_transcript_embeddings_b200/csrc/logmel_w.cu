@@ -28,6 +28,7 @@
 #include "stx_common.h"
 #include "codelets.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <cstddef>
 #include <mutex>
 
@@ -57,6 +58,13 @@ struct WTables {
     int   melfirst[kMel];
 };
 
+// One 32-frame tile of a work item (clip b, chunk of frames), kept in shared memory and read where it is used
+struct WTile {
+    const float* clip; float* out_b; unsigned* cmax;
+    int len, t0, t_end, item;
+    float peak;
+    int aligned, valid, last;           // last: the item ends with this tile (publish the running maximum)
+};
 struct Smem {
     float2 ex[12][16][kTile];           // pass-1 rows k1 = 1..12: [k1 - 1][n2][lane]
     float  ex0[16][kTile];              // row k1 = 0 (real)
@@ -67,7 +75,7 @@ struct Smem {
     float  stage[kTileSamples];         // raw PCM of the next tile (cp.async.bulk)
     float  melw[kMelWeights];
     int    melfirst[kMel];
-    float  wmax[kWarps];
+    WTile  desc[2];                     // the tile in flight and the next one (written by thread 0)
     unsigned long long mbar;
 };
 static_assert(sizeof(Smem) + 1024 <= 233472 / 2, "two CTAs per SM: 2 x (dynamic + 1 KB reserved) <= 228 KB");
@@ -152,36 +160,55 @@ __device__ __forceinline__ float max_unkey(unsigned k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// PERSISTENT: two CTAs per SM, every CTA streams through the work items (clip b, chunk of chunk_frames frames) blockIdx.x,
+// blockIdx.x + gridDim.x, ...: tables, barrier initialisation and the pipeline fill are paid once per kernel instead of
+// once per chunk (1.5 us each, 9 % of the non-persistent form), and the PCM of an item's first tile lands while the
+// previous item's last tile is transformed.
 __global__ void __launch_bounds__(kThreads, 2)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
-         const float* __restrict__ peaks, const WTables* __restrict__ tab, int n_samples, int chunk_frames,
-         float* __restrict__ out, unsigned* __restrict__ clip_max) {
+         const float* __restrict__ peaks, const WTables* __restrict__ tab, int B, int n_samples, int chunk_frames,
+         int chunks_per_clip, float* __restrict__ out, unsigned* __restrict__ clip_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
-    const int b = blockIdx.y;
     const int T = n_samples / kHop;
-    const int t_begin = blockIdx.x * chunk_frames;
-    if (t_begin >= T) return;
-    const int t_end = min(T, t_begin + chunk_frames);
-    const int len = min(lengths[b], n_samples);
-    const float* clip = pcm + offsets[b];
-    const bool aligned = (reinterpret_cast<unsigned long long>(clip) & 15ull) == 0;
-    const float peak = peaks ? peaks[b] : 1.0f;
-    float* out_b = out + (size_t)b * kMel * T;
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int items = B * chunks_per_clip;
 
+    // (thread 0 only) first tile of the item; every item is non-empty (all clips are padded to n_samples)
+    auto open_item = [&](int item, WTile& d) {
+        d.valid = 0; d.last = 0; d.item = item;
+        if (item < items) {
+            const int b = item / chunks_per_clip, chunk = item - b * chunks_per_clip;
+            d.valid = 1; d.t0 = chunk * chunk_frames; d.t_end = min(T, d.t0 + chunk_frames);
+            d.len = min(__ldg(lengths + b), n_samples);
+            d.clip = pcm + __ldg(offsets + b);
+            d.aligned = (reinterpret_cast<unsigned long long>(d.clip) & 15ull) == 0;
+            d.peak = peaks ? __ldg(peaks + b) : 1.0f;
+            d.out_b = out + (size_t)b * kMel * T;
+            d.cmax = clip_max + b;
+        }
+    };
+    auto next_tile = [&](WTile& c, WTile& d) {       // (thread 0 only) d = the tile after c
+        if (c.t0 + kTile < c.t_end) { d = c; d.t0 += kTile; c.last = 0; }
+        else { open_item(c.item + (int)gridDim.x, d); c.last = 1; }
+    };
+    auto prefetch = [&](const WTile& d) {           // (thread 0 only) the tile's PCM -> staging; nothing for padding-only tiles
+        if (d.valid) {
+            const int g0 = d.t0 * kHop - kN / 2;
+            const StageRange sr = stage_range(g0, d.len, d.aligned != 0);
+            if (sr.hi > sr.lo) {
+                mbar_expect_tx(&sm.mbar, (unsigned)(sr.hi - sr.lo) * 4u);
+                bulk_g2s(sm.stage + (sr.lo - g0), d.clip + sr.lo, (unsigned)(sr.hi - sr.lo) * 4u, &sm.mbar);
+            }
+        }
+    };
     if (tid == 0) {
         mbar_init(&sm.mbar, 1);
-        const int g0 = t_begin * kHop - kN / 2;
-        const StageRange sr = stage_range(g0, len, aligned);
-        if (sr.hi > sr.lo) {
-            mbar_expect_tx(&sm.mbar, (unsigned)(sr.hi - sr.lo) * 4u);
-            bulk_g2s(sm.stage + (sr.lo - g0), clip + sr.lo, (unsigned)(sr.hi - sr.lo) * 4u, &sm.mbar);
-        }
+        open_item(blockIdx.x, sm.desc[0]);
+        prefetch(sm.desc[0]);
     }
     for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
     if (tid < kMel) sm.melfirst[tid] = tab->melfirst[tid];
@@ -189,11 +216,19 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
 
     float run_max = __int_as_float(0xff800000);
     unsigned parity = 0;
+    int slot = 0;
 
-    for (int t0 = t_begin; t0 < t_end; t0 += kTile) {
+    while (sm.desc[slot].valid) {
+        const WTile& cur = sm.desc[slot];
+        const int t0 = cur.t0, t_end = cur.t_end, len = cur.len;
+        const float* clip = cur.clip;
+        const bool aligned = cur.aligned != 0;
+        const float peak = cur.peak;
+        float* out_b = cur.out_b;
         // ---- layout: zero padding to n_samples, reflect padding of 200 around it, peak divisor; rows of 161 ----
         const int g0 = t0 * kHop - kN / 2;
-        if (g0 >= len && len <= n_samples - (kN / 2 + 2)) {
+        const bool padding_only = g0 >= len && len <= n_samples - (kN / 2 + 2);
+        if (padding_only) {
             // the whole tile lies in the zero padding behind the clip (and the reflected tail of the padded signal is
             // zero as well): every mel energy is 0, so every value is log10 of the floor; no copy was issued for it
             const float v = log10_pos(1e-10f);
@@ -203,8 +238,13 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 for (int i = 0; i < 10; ++i) out_b[(size_t)(warp + 8 * i) * T + t] = v;
                 run_max = fmaxf(run_max, v);
             }
-            continue;
-        }
+            __syncthreads();                        // every warp is done with the previous tile's descriptor (the other slot)
+            if (tid == 0) {
+                next_tile(sm.desc[slot], sm.desc[slot ^ 1]);
+                prefetch(sm.desc[slot ^ 1]);
+            }
+            __syncthreads();                        // the next descriptor and `last` are visible
+        } else {
         const StageRange sr = stage_range(g0, len, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         if (sr.lo == g0 && sr.hi == g0 + kTileSamples && peak == 1.0f) {
@@ -235,12 +275,9 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         }
         __syncthreads();                            // xs ready; staging is free
 
-        if (tid == 0 && t0 + kTile < t_end) {
-            const StageRange nx = stage_range(g0 + kTile * kHop, len, aligned);
-            if (nx.hi > nx.lo) {
-                mbar_expect_tx(&sm.mbar, (unsigned)(nx.hi - nx.lo) * 4u);
-                bulk_g2s(sm.stage + (nx.lo - (g0 + kTile * kHop)), clip + nx.lo, (unsigned)(nx.hi - nx.lo) * 4u, &sm.mbar);
-            }
+        if (tid == 0) {                             // the next tile (of this item or the next): descriptor, then its PCM
+            next_tile(sm.desc[slot], sm.desc[slot ^ 1]);
+            prefetch(sm.desc[slot ^ 1]);
         }
 
         // ---- window + pass 1 (role = n2 = warp, warp + 8) ----
@@ -314,17 +351,14 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             }
         }
         __syncthreads();                            // the power spectrum is consumed: the next layout pass may overwrite it
-    }
-
+        }
+        if (cur.last) {                             // the item is complete: one atomic per warp publishes the clip's running maximum
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
-    if (lane == 0) sm.wmax[warp] = run_max;
-    __syncthreads();
-    if (tid == 0) {
-        float m = sm.wmax[0];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) m = fmaxf(m, sm.wmax[w]);
-        atomicMax(clip_max + b, max_key(m));
+            for (int o = 16; o > 0; o >>= 1) run_max = fmaxf(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
+            if (lane == 0) atomicMax(cur.cmax, max_key(run_max));
+            run_max = __int_as_float(0xff800000);
+        }
+        slot ^= 1;
     }
 }
 
@@ -453,10 +487,16 @@ int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_
         STX_CUDA(cudaGetDevice(&dev));
         STX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const int chunk_frames = pick_chunk(B, T, sms);
-    STX_LAUNCH(w_frames, dim3((T + chunk_frames - 1) / chunk_frames, B), dim3(kThreads), sizeof(Smem), st,
-               d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, n_samples, chunk_frames,
-               d_out, clip_max);
+    int chunk_frames = pick_chunk(B, T, sms);
+    if (const char* e = std::getenv("STX_W_CHUNK")) {        // development: force the frames per CTA (a multiple of 32, >= 32)
+        const int v = std::atoi(e);
+        if (v >= kTile && v % kTile == 0) chunk_frames = v;
+    }
+    const int chunks = (T + chunk_frames - 1) / chunk_frames;
+    const int grid = (int)std::min<long long>(2LL * sms, (long long)B * chunks);
+    STX_LAUNCH(w_frames, dim3(grid), dim3(kThreads), sizeof(Smem), st,
+               d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, n_samples, chunk_frames,
+               chunks, d_out, clip_max);
     const size_t total = (size_t)kMel * T;
     const int gx = (int)std::max<size_t>(1, std::min<size_t>((total / 4 + 255) / 256, 64));
     STX_LAUNCH(w_finish, dim3(gx, B), dim3(256), 0, st, d_lengths, clip_max, n_samples, d_out, d_mask);
