@@ -15,8 +15,8 @@
 //   rs_decim<DOWN>  up == 1 (48 k -> 16 k, 32 k -> 16 k, 96 k, 64 k): every output uses the same 20 * DOWN + 1 taps.  A thread
 //                   computes 4 consecutive outputs from one register window of the input, with the taps broadcast from
 //                   shared memory as float4: 1 + DOWN shared loads per 4 x 4 FMAs instead of 2 per FMA
-//   rs_poly         any up / down: per-output phase, filter bank in shared memory (rows of odd length: lanes with
-//                   different phases hit different banks)
+//   rs_poly         any up / down: a thread owns four outputs of equal phase (m, m + up, ...), filter bank in shared memory
+//                   with float4 tap loads
 // The per-clip max |y| (the peak-normalise of R/processor.py:91-92 needs it next) is reduced in the same pass.
 #include "stx_common.h"
 #include <cmath>
@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kXsMax = 6400;             // floats of staged input per CTA (25 KB: several CTAs per SM overlap staging and filtering)
-constexpr int kBankSmemMax = 14336;      // floats of filter bank kept in shared memory (56 KB); larger banks are read through L1
+constexpr int kBankSmemMax = 18432;      // floats of filter bank kept in shared memory (72 KB); larger banks are read through L1
 
 struct Plan {
     int up, down, J, Jp, n_pre_remove, L;
@@ -76,7 +76,8 @@ void design(int up, int down, Plan& pl) {
     pl.h_pad.assign(pl.L, 0.0f);
     for (int i = 0; i < numtaps; ++i) pl.h_pad[n_pre_pad + i] = (float)(h[i] / sum) * (float)up;
     pl.J = (pl.L + up - 1) / up;
-    pl.Jp = pl.J | 1;                    // odd row length
+    pl.Jp = 4 * (((pl.J + 3) / 4) | 1);  // rows of 4 (2 i + 1) floats: float4 loads, and rows of different phases start in
+                                         // different 16-byte bank groups
 }
 
 std::mutex g_plan_mutex;
@@ -137,23 +138,30 @@ __device__ __forceinline__ void stage_input(float* xs, const float* __restrict__
 }
 
 // ---- general up / down --------------------------------------------------------------------------
+// Outputs m and m + up have the SAME phase and inputs exactly `down` samples apart, so a thread owns kR = 4 outputs
+// m, m + up, m + 2 up, m + 3 up: every float4 of taps (one LDS.128; rows of the bank are Jp = 4 (2 i + 1) floats long, so
+// lanes of different phases hit different bank groups) feeds 16 FMAs, against one tap load per FMA when every output
+// fetches its own taps.  A CTA tile is kR * up * Q consecutive outputs (Q = groups of `up` base outputs).
+constexpr int kR = 4;
 template <bool kBankSmem>
 __global__ void __launch_bounds__(kThreads)
 rs_poly(const float* __restrict__ in, const long long* __restrict__ in_off, const int* __restrict__ in_len,
         const long long* __restrict__ out_off, const int* __restrict__ out_len, const float* __restrict__ bank,
-        int up, int down, int J, int Jp, int n_pre_remove, int out_tile, float* __restrict__ out, float* __restrict__ peaks) {
+        int up, int down, int J4, int Jp, int n_pre_remove, int Q, float* __restrict__ out, float* __restrict__ peaks) {
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* bank_s = smem + kXsMax;
     const int b = blockIdx.y;
     const int n_out = out_len[b];
+    const int out_tile = kR * up * Q;
     const int m0 = blockIdx.x * out_tile;
     if (m0 >= n_out) return;
     const int m1 = min(n_out, m0 + out_tile);
     const int n = in_len[b];
     const float* clip = in + in_off[b];
+    const int J = 4 * J4;                                              // taps per phase, padded with zeros to a multiple of 4
     const long long i_lo = ((long long)(m0 + n_pre_remove) * down) / up - (J - 1);
-    const long long i_hi = ((long long)(m1 - 1 + n_pre_remove) * down) / up;
+    const long long i_hi = ((long long)(m0 + out_tile - 1 + n_pre_remove) * down) / up;      // whole tile: companions may lie past m1
     stage_input(xs, clip, i_lo, (int)(i_hi - i_lo + 1), n);
     if (kBankSmem)
         for (int k = threadIdx.x; k < up * Jp; k += kThreads) bank_s[k] = __ldg(bank + k);
@@ -161,24 +169,31 @@ rs_poly(const float* __restrict__ in, const long long* __restrict__ in_off, cons
     const float* bk = kBankSmem ? bank_s : bank;
     float* o = out + out_off[b];
     float peak = 0.0f;
-    for (int m = m0 + threadIdx.x; m < m1; m += kThreads) {
+    for (int w = threadIdx.x; w < up * Q; w += kThreads) {
+        const int q = w / up, base = w - q * up;
+        const int m = m0 + q * kR * up + base;                         // this thread's outputs: m + k * up, k = 0 .. kR - 1
+        if (m >= m1) continue;
         const long long p = (long long)(m + n_pre_remove) * down;
         const long long i0 = p / up;
         const int ph = (int)(p - i0 * up);
-        const float* hb = bk + (size_t)ph * Jp;
+        const float4* hb = reinterpret_cast<const float4*>(bk + (size_t)ph * Jp);
         const float* xr = xs + (int)(i0 - i_lo);
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        int j = 0;
-        for (; j + 4 <= J; j += 4) {
-            a0 = fmaf(hb[j + 0], xr[-j - 0], a0);
-            a1 = fmaf(hb[j + 1], xr[-j - 1], a1);
-            a2 = fmaf(hb[j + 2], xr[-j - 2], a2);
-            a3 = fmaf(hb[j + 3], xr[-j - 3], a3);
+        float acc[kR] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 2
+        for (int j4 = 0; j4 < J4; ++j4) {
+            const float4 h = hb[j4];
+#pragma unroll
+            for (int k = 0; k < kR; ++k) {
+                const float* x = xr + k * down - 4 * j4;
+                acc[k] = fmaf(h.x, x[0], acc[k]);
+                acc[k] = fmaf(h.y, x[-1], acc[k]);
+                acc[k] = fmaf(h.z, x[-2], acc[k]);
+                acc[k] = fmaf(h.w, x[-3], acc[k]);
+            }
         }
-        for (; j < J; ++j) a0 = fmaf(hb[j], xr[-j], a0);
-        const float y = (a0 + a1) + (a2 + a3);
-        o[m] = y;
-        peak = fmaxf(peak, fabsf(y));
+#pragma unroll
+        for (int k = 0; k < kR; ++k)
+            if (m + k * up < m1) { o[m + k * up] = acc[k]; peak = fmaxf(peak, fabsf(acc[k])); }
     }
     if (peaks) clip_peak(peak, peaks, b);
 }
@@ -333,9 +348,12 @@ int stx_resample_poly(const float* d_in, const int64_t* d_in_offsets, const int3
         }
     }
 
-    // general case: the tile's input window must fit the staging buffer
-    long long out_tile = ((long long)(kXsMax - pl->J - 4) * up) / down;
-    out_tile = std::max<long long>(1, std::min<long long>(out_tile, 1024));
+    // general case: a tile is kR * up * Q outputs whose input window must fit the staging buffer
+    const int J4 = (pl->J + 3) / 4;
+    long long Q = ((long long)(kXsMax - 4 * J4 - 4) * up / down) / ((long long)kR * up);
+    Q = std::min<long long>(Q, std::max<long long>(1, (3 * kThreads) / up));       // about three work items per thread
+    if (Q < 1) { set_error("stx_resample_poly: %d -> %d Hz: one tile of %d outputs does not fit the staging buffer", orig_sr, target_sr, kR * up); return STX_EINVAL; }
+    const long long out_tile = (long long)kR * up * Q;
     const dim3 grid((unsigned)((max_out_length + out_tile - 1) / out_tile), B);
     const bool bank_smem = (long long)up * pl->Jp <= kBankSmemMax;
     static bool attr_done[64] = {false};
@@ -348,11 +366,11 @@ int stx_resample_poly(const float* d_in, const int64_t* d_in_offsets, const int3
     }
     if (bank_smem) {
         STX_LAUNCH(rs_poly<true>, grid, dim3(kThreads), (size_t)(kXsMax + up * pl->Jp) * sizeof(float), st, d_in, in_off,
-                   d_in_lengths, out_off, d_out_lengths, pl->d_bank, up, down, pl->J, pl->Jp, pl->n_pre_remove, (int)out_tile,
+                   d_in_lengths, out_off, d_out_lengths, pl->d_bank, up, down, J4, pl->Jp, pl->n_pre_remove, (int)Q,
                    d_out, d_peaks);
     } else {
         STX_LAUNCH(rs_poly<false>, grid, dim3(kThreads), (size_t)kXsMax * sizeof(float), st, d_in, in_off, d_in_lengths,
-                   out_off, d_out_lengths, pl->d_bank, up, down, pl->J, pl->Jp, pl->n_pre_remove, (int)out_tile, d_out, d_peaks);
+                   out_off, d_out_lengths, pl->d_bank, up, down, J4, pl->Jp, pl->n_pre_remove, (int)Q, d_out, d_peaks);
     }
     return 0;
 }
