@@ -45,6 +45,43 @@ def make_feature_extractor(audio_model_name: str, device=None, **kwargs):
                      "(supported: facebook/w2v-bert-2.0 family, openai/whisper-*)")
 
 
+def load_audio(audio_path):
+    """``librosa.load(audio_path, sr=None)`` (R/processor.py:74): (float32 mono array, native sampling rate).
+
+    Decoding is the step before the hot path and stays with librosa when it is installed (any format it reads).  Without
+    librosa, uncompressed RIFF/WAVE files (8/16/24/32-bit PCM) are decoded here with the standard library, with the scaling
+    libsndfile applies (full scale = 1.0, i.e. int16 / 32768) and librosa's channel average for multi-channel files;
+    anything else raises, it is never approximated."""
+    try:
+        import librosa
+    except ImportError:
+        librosa = None
+    if librosa is not None:
+        return librosa.load(audio_path, sr=None)
+    import wave
+    try:
+        with wave.open(str(audio_path), "rb") as w:
+            sr, ch, width, frames = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(frames)
+    except (wave.Error, EOFError) as e:
+        raise ImportError(f"decoding {audio_path!r} needs librosa, as in the reference (only PCM WAV files are read without it)") from e
+    if width == 1:
+        x = (np.frombuffer(raw, np.uint8).astype(np.float32) - 128.0) / 128.0
+    elif width == 2:
+        x = np.frombuffer(raw, "<i2").astype(np.float32) / 32768.0
+    elif width == 3:
+        b = np.frombuffer(raw, np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        x = np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float32) / 8388608.0
+    elif width == 4:
+        x = (np.frombuffer(raw, "<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+    else:
+        raise ImportError(f"{audio_path!r}: {8 * width}-bit WAV needs librosa")
+    if ch > 1:
+        x = x.reshape(-1, ch).mean(axis=1, dtype=np.float32)           # librosa.load(mono=True)
+    return np.ascontiguousarray(x, np.float32), int(sr)
+
+
 class AudioTextProcessor:
     """Handles audio processing and scoring for the audio-text model on a B200."""
 
@@ -87,11 +124,8 @@ class AudioTextProcessor:
 
     # -- audio -----------------------------------------------------------------------------------
     def process_audio_file(self, audio_path):
-        try:
-            import librosa
-        except ImportError as e:  # decoding is the step before the hot path
-            raise ImportError("process_audio_file needs librosa to decode audio files, as in the reference") from e
-        audio_array, orig_sr = librosa.load(audio_path, sr=None)
+        """R/processor.py:69-77: decode at the file's own rate (``librosa.load(path, sr=None)``), then process_audio_array."""
+        audio_array, orig_sr = load_audio(audio_path)
         return self.process_audio_array(audio_array, orig_sr)
 
     def _prepare(self, audio_array, orig_sr):

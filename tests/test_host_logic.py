@@ -95,3 +95,28 @@ def test_chunk_bounds_cover_every_clip_once():
                 assert (offsets[b1 - 1] + lengths[b1 - 1] - offsets[b0]) * 4 <= chunk_bytes
     assert len(fe.chunk_bounds(offsets, lengths, 1)) == lengths.size
     assert len(fe.chunk_bounds(offsets, lengths, 1 << 40)) == 1
+
+
+def test_load_audio_reads_pcm_wav_without_librosa(tmp_path):
+    """process_audio_file's decode step (R/processor.py:74) for uncompressed WAV when librosa is absent: libsndfile scaling,
+    channel average, native sampling rate."""
+    import wave
+    from speech_transcript_embeddings_b200.processor import load_audio
+    try:
+        import librosa  # noqa: F401
+        pytest.skip("librosa installed: the reference's own decoder is used")
+    except ImportError:
+        pass
+    rng = np.random.default_rng(0)
+    pcm = rng.integers(-32768, 32767, size=(4800, 2), dtype=np.int16)
+    path = tmp_path / "a.wav"
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(48000)
+        w.writeframes(pcm.tobytes())
+    x, sr = load_audio(path)
+    assert sr == 48000 and x.dtype == np.float32 and x.shape == (4800,)
+    assert np.array_equal(x, (pcm.astype(np.float32) / 32768.0).mean(axis=1, dtype=np.float32))
+    bad = tmp_path / "b.mp3"
+    bad.write_bytes(b"ID3\x03" + bytes(64))
+    with pytest.raises(ImportError):
+        load_audio(bad)

@@ -54,3 +54,25 @@ def test_compute_similarity(cuda_device):
 def test_unsupported_audio_model_is_an_error(cuda_device):
     with pytest.raises(ValueError):
         AudioTextProcessor(audio_model_name="facebook/wav2vec2-base", device=cuda_device)
+
+
+def test_process_audio_file_wav_48k(cuda_device, tmp_path):
+    """R/processor.py:69-77 end to end on a 48 kHz 16-bit WAV: decode, device resampling, peak rule, recipe K."""
+    import wave
+    from oracle import resample as OR
+    from speech_transcript_embeddings_b200.processor import load_audio
+    x = (synth.clip("G", 60000, 9) * 3.0).clip(-1.0, 32767.0 / 32768.0)
+    pcm = np.round(x * 32768.0).astype(np.int16)
+    path = tmp_path / "clip48k.wav"
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(48000)
+        w.writeframes(pcm.tobytes())
+    audio, sr = load_audio(path)
+    assert sr == 48000 and audio.dtype == np.float32
+    got = AudioTextProcessor(device=cuda_device).process_audio_file(str(path))
+    xr = OR.resample_poly(audio, 48000, 16000)
+    if np.abs(xr).max() > 1.0:
+        xr = xr / np.abs(xr).max()
+    ref, mask = OK.extract([xr])
+    assert np.abs(got["input_features"].cpu().numpy() - ref).max() <= 1e-4
+    assert np.array_equal(got["attention_mask_audio"].cpu().numpy(), mask)
