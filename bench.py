@@ -297,8 +297,8 @@ def run_b200(args):
         ev1.record(torch.cuda.current_stream(dev))
         launches_timed = _lib.launch_count() - launches0
         barrier()
-        # same work for one more second so that nvidia-smi (100 ms cadence) samples the clocks under this load
-        t_end = time.perf_counter() + 1.0
+        # same work for two more seconds so that nvidia-smi (100 ms cadence, but 0.2-1 s per call on some boxes) samples the clocks under this load
+        t_end = time.perf_counter() + 2.0
         extra = 0
         while time.perf_counter() < t_end:
             step_device(extra)
