@@ -271,7 +271,8 @@ def run_b200(args):
 
         def step_device(i):
             pcm_d, off_d, len_d = dev_batches[i % POOL_BATCHES]
-            ops.fbank_k(pcm_d, off_d, len_d, n, T_pad, out=outs[i % POOL_BATCHES], mask=masks[i % POOL_BATCHES])
+            ops.fbank_k(pcm_d, off_d, len_d, n, T_pad, out=outs[i % POOL_BATCHES], mask=masks[i % POOL_BATCHES],
+                        uniform=True)      # every clip of the cfg2 batch has n samples
         bytes_per_clip = K_BYTES_PER_CLIP
         dominant = "k_frames<false>"
     else:

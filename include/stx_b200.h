@@ -80,7 +80,10 @@ int64_t     stx_get_table(const char* name, double* h_out, int64_t cap);
  *   d_pcm      packed float32 PCM of all clips (NOT pre-scaled by 2^15)
  *   d_offsets  [B] start sample of each clip inside d_pcm (int64); multiples of 4 recommended
  *   d_lengths  [B] samples per clip (int32).  T_b = 1 + (len-400)/160 frames (0 if len < 400)
- *   max_length host copy of max_b len (sizes the grid; no device->host sync is ever made)
+ *   max_length host copy of max_b len (sizes the grid; no device->host sync is ever made).  Passed NEGATED it is a promise
+ *              that EVERY clip has exactly -max_length samples (e.g. a batch cut to equal windows): the library then skips
+ *              the small device-side pass that compacts the work items of ragged batches.  A wrong promise costs load
+ *              balance, never correctness
  *   d_peak     NULL, or [B] float32 divisors: sample = pcm / d_peak[b] in float32 before
  *              anything else (the reference's peak-normalise, R/processor.py:91-92)
  *   T_pad      EVEN number of raw frames per clip in the padded output (TF .pad with

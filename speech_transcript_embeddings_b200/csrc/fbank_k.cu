@@ -45,6 +45,7 @@
 #include "codelets.cuh"
 #include <cmath>
 #include <cstddef>
+#include <cstdint>
 #include <cstdlib>
 #include <mutex>
 
@@ -544,7 +545,7 @@ template <bool kPeak>
 __global__ void __launch_bounds__(kThreads, 1)
 k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
              const float* __restrict__ peaks, const KTables* __restrict__ tab, int B, int T_pad, int chunk_frames,
-             int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials) {
+             int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials, const int* __restrict__ sched) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemDuo& sm = *reinterpret_cast<SmemDuo*>(smem_raw);
 
@@ -560,22 +561,27 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     unsigned long long* red = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(&sg.ex[0][0][0]) + kRedOff);
 
     // PERSISTENT: the grid is one CTA per SM and every GROUP streams through its own list of work items, item =
-    // (clip b, chunk of chunk_frames frames), items G, G + groups, G + 2 groups, ... with G = 2 blockIdx.x + g.  The TMEM
+    // (clip b, chunk of chunk_frames frames) from the schedule, positions G, G + groups, ... with G = 2 blockIdx.x + g.  The TMEM
     // allocation, the tables and the pipeline fill are paid once per kernel instead of once per chunk (2.3 us each, 7 % of
     // the non-persistent form), and the groups never meet again after the first barrier, so they drift into complementary
     // phases on their own.
-    const int items = B * chunks_per_clip;
     const int item_step = 2 * gridDim.x;
-    // (thread 0 of the group only) first tile of the first non-empty item at or after `item` in this group's list
-    auto open_item = [&](int item, TileDesc& d) {
-        d.valid = 0; d.last = 0; d.item = item;
-        for (; item < items; item += item_step) {
+    // (thread 0 of the group only) first tile of the work item at position `pos` of the schedule k_schedule wrote:
+    // sched[0] = number of NON-EMPTY items, sched[1 + pos] = b * chunks_per_clip + chunk.  Group G takes positions G,
+    // G + groups, ...: every group gets the same number of non-empty items (+- 1) however ragged the batch is
+    // Without a schedule (sched == nullptr: the caller vouches that all clips have the same length, so every item is
+    // non-empty and the plain round-robin over all items is already balanced) positions are item numbers.
+    auto open_item = [&](int pos, TileDesc& d) {
+        const int n_pos = sched ? __ldg(sched) : B * chunks_per_clip;
+        d.valid = 0; d.last = 0; d.item = pos;
+        for (; pos < n_pos; pos += item_step) {
+            const int item = sched ? __ldg(sched + 1 + pos) : pos;
             const int b = item / chunks_per_clip, chunk = item - b * chunks_per_clip;
             const int n = __ldg(lengths + b);
             const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
             const int t_begin = chunk * chunk_frames;
-            if (t_begin >= T) continue;
-            d.valid = 1; d.item = item; d.n = n; d.t0 = t_begin; d.t_end = min(T, t_begin + chunk_frames);
+            if (t_begin >= T) continue;              // (only without a schedule, and only if the caller's promise was wrong)
+            d.valid = 1; d.item = pos; d.n = n; d.t0 = t_begin; d.t_end = min(T, t_begin + chunk_frames);
             d.clip = pcm + __ldg(offsets + b);
             d.aligned = (reinterpret_cast<unsigned long long>(d.clip) & 15ull) == 0;
             d.peak = kPeak ? __ldg(peaks + b) : 1.0f;
@@ -613,6 +619,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                // mbarrier init, tables, TMEM base visible
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // the schedule (k_schedule, the programmatic primary, if any) is complete
     if (tl == 0) {
         open_item(2 * blockIdx.x + g, sg.desc[0]);
         prefetch(sg.desc[0]);
@@ -856,6 +863,55 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     }
 }
 
+// The work items of k_frames_duo, compacted: sched[0] = number of non-empty items, sched[1 + i] = b * chunks_per_clip + chunk in
+// clip-major order.  One CTA; a block-wide exclusive scan of the per-clip chunk counts, 1024 clips at a time.  (Lengths live
+// on the device, so the host cannot do this; without it the static round-robin over ALL items leaves the busiest group of a
+// ragged batch with a third more tiles than the average.)
+__global__ void __launch_bounds__(1024)
+k_schedule(const int* __restrict__ lengths, int B, int chunk_frames, int chunks_per_clip, int* __restrict__ sched) {
+    // programmatic dependent launch: k_frames_duo may start its prologue (TMEM allocation, tables) right away; it waits for
+    // this grid's completion (griddepcontrol.wait) before it reads the schedule
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ int s_warp[32];
+    __shared__ int s_off[1024], s_cnt[1024];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + tid;
+        int cnt = 0;
+        if (b < B) {
+            const int n = lengths[b];
+            const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+            cnt = (T + chunk_frames - 1) / chunk_frames;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+            s_warp[lane] = w;                        // inclusive scan of the warp totals
+        }
+        __syncthreads();
+        s_off[tid] = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - cnt;
+        s_cnt[tid] = cnt;
+        __syncthreads();
+        // one warp per clip writes that clip's items: coalesced, and as parallel as the batch is wide
+        const int nclips = min(1024, B - base);
+        for (int i = warp; i < nclips; i += 32)
+            for (int c = lane; c < s_cnt[i]; c += 32) sched[1 + s_off[i] + c] = (base + i) * chunks_per_clip + c;
+        __syncthreads();
+        if (tid == 0) s_carry += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) sched[0] = s_carry;
+}
+
 // in-place CMVN + padding rows + mask.  One thread per float4 of a clip's [T_pad, 80] block.
 //   rows t < T            normalised features
 //   rows T <= t < T2      padding_value (T2 = T rounded up to even: the half of the last stacked frame of an odd clip)
@@ -1052,6 +1108,24 @@ inline int pick_chunk_duo(int B, int max_frames, int sms) {
     }
     return best;
 }
+// k_frames_duo is launched as the programmatic dependent of k_schedule: its CTAs start while the (one-CTA) scheduler still
+// runs and block in griddepcontrol.wait only where they first read the schedule
+template <typename K, typename... Args>
+int launch_dependent(const char* name, K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const bool prof = g_profile.load(std::memory_order_relaxed) != 0;
+    if (prof) profile_before(name, st);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (prof) profile_after(st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return 0;
+}
 inline bool use_duo() {
     static const bool v = [] { const char* e = std::getenv("STX_K_SINGLE"); return !(e && e[0] == '1'); }();
     return v;
@@ -1065,9 +1139,12 @@ extern "C" {
 
 int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     using namespace stx;
-    if (B < 0 || max_length < 0 || !bytes) { set_error("stx_fbank_k_workspace: bad argument"); return STX_EINVAL; }
+    if (B < 0 || max_length == INT32_MIN || !bytes) { set_error("stx_fbank_k_workspace: bad argument"); return STX_EINVAL; }
+    if (max_length < 0) max_length = -max_length;          // the "uniform batch" form of stx_fbank_k
     const int chunks = (frames_of(max_length) + kMinChunk - 1) / kMinChunk;
-    *bytes = align256(size_t(B) * std::max(chunks, 1) * kStatWords * sizeof(long long));
+    // per-chunk statistics partials, then the schedule of k_frames_duo (item count + one int per item)
+    *bytes = align256(size_t(B) * std::max(chunks, 1) * kStatWords * sizeof(long long)) +
+             align256(sizeof(int) * (1 + size_t(B) * std::max(chunks, 1)));
     return 0;
 }
 
@@ -1075,7 +1152,11 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
                         const float* d_peak, int T_pad, float padding_value, float tail_value, int normalize,
                         float* d_out, void* d_mask, int mask_mode, void* d_ws, size_t ws_bytes, void* stream) {
     using namespace stx;
-    if (B < 0 || max_length < 0 || T_pad < 0 || (T_pad & 1)) { set_error("stx_fbank_k: B, max_length >= 0 and even T_pad required"); return STX_EINVAL; }
+    // max_length < 0: the caller promises that EVERY clip has exactly -max_length samples
+    const bool uniform = max_length < 0;
+    if (max_length == INT32_MIN) { set_error("stx_fbank_k: bad max_length"); return STX_EINVAL; }
+    if (uniform) max_length = -max_length;
+    if (B < 0 || T_pad < 0 || (T_pad & 1)) { set_error("stx_fbank_k: B >= 0 and even T_pad >= 0 required"); return STX_EINVAL; }
     if (B == 0 || T_pad == 0) return 0;
     if (!d_pcm || !d_offsets || !d_lengths || !d_out || !d_ws) { set_error("stx_fbank_k: null pointer"); return STX_EINVAL; }
     if (int rc = check_device()) return rc;
@@ -1102,16 +1183,23 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
     }
     const int chunks = std::max((max_frames + chunk_frames - 1) / chunk_frames, 1);
     long long* partials = static_cast<long long*>(d_ws);
+    const int chunks64 = std::max((frames_of(max_length) + kMinChunk - 1) / kMinChunk, 1);
+    int* sched = reinterpret_cast<int*>(static_cast<unsigned char*>(d_ws) + align256(size_t(B) * chunks64 * kStatWords * sizeof(long long)));
     if (frames_of(max_length) > 0) {
         const int duo_grid = (int)std::min<long long>(sms, ((long long)B * chunks + 1) / 2);
-        if (duo && d_peak) {
-            STX_LAUNCH(k_frames_duo<true>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
-                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, T_pad,
-                       chunk_frames, chunks, d_out, partials);
-        } else if (duo) {
-            STX_LAUNCH(k_frames_duo<false>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
-                       d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, T_pad,
-                       chunk_frames, chunks, d_out, partials);
+        // uniform batch (the caller's promise): no empty items, the plain round-robin is balanced, and the 3.6 us of
+        // k_schedule are saved; a wrong promise only costs load balance, never correctness
+        const bool scheduled = duo && !uniform && B > 1;
+        if (scheduled) STX_LAUNCH(k_schedule, dim3(1), dim3(1024), 0, st, d_lengths, B, chunk_frames, chunks, sched);
+        const int* sched_arg = scheduled ? sched : nullptr;
+        if (duo) {
+            const long long* off = reinterpret_cast<const long long*>(d_offsets);
+            const int rc = d_peak
+                ? launch_dependent("k_frames_duo<true>", k_frames_duo<true>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
+                                   d_pcm, off, d_lengths, d_peak, tab, B, T_pad, chunk_frames, chunks, d_out, partials, sched_arg)
+                : launch_dependent("k_frames_duo<false>", k_frames_duo<false>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
+                                   d_pcm, off, d_lengths, d_peak, tab, B, T_pad, chunk_frames, chunks, d_out, partials, sched_arg);
+            if (rc) return rc;
         } else if (d_peak) {
             STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
                        d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, T_pad,

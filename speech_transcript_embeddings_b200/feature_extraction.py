@@ -384,9 +384,11 @@ class B200SeamlessM4TFeatureExtractor(_B200ExtractorBase):
             h_mask = torch.empty((B, T_pad // 2), dtype=torch.int32, pin_memory=True) if return_attention_mask else None
 
             def launch(pcm_c, off_c, len_c, b0, b1, max_len):
+                lens_c = packed.lengths[b0:b1]
                 ops.fbank_k(pcm_c, off_c, len_c, max_len, T_pad, self.padding_value, bool(do_normalize_per_mel_bins),
                             want_mask=bool(return_attention_mask), out=feats[b0:b1],
-                            mask=mask[b0:b1] if mask is not None else None)
+                            mask=mask[b0:b1] if mask is not None else None,
+                            uniform=bool(lens_c.size and lens_c.min() == lens_c.max()))
 
             self._pipeline(packed, launch, [(feats, h_feats)] + ([(mask, h_mask)] if mask is not None else []))
             data = {"input_features": h_feats}
@@ -395,7 +397,8 @@ class B200SeamlessM4TFeatureExtractor(_B200ExtractorBase):
             return self._finish(data, to_numpy)
         pcm_d, off_d, len_d = self.to_device(packed)
         feats, mask = ops.fbank_k(pcm_d, off_d, len_d, packed.max_length, T_pad, self.padding_value,
-                                  bool(do_normalize_per_mel_bins), want_mask=bool(return_attention_mask))
+                                  bool(do_normalize_per_mel_bins), want_mask=bool(return_attention_mask),
+                                  uniform=bool(B and packed.lengths.min() == packed.lengths.max()))
         data = {"input_features": feats}
         if return_attention_mask:
             data["attention_mask"] = mask

@@ -124,12 +124,14 @@ def resample_poly(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tenso
 
 def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_length: int, T_pad: int,
             padding_value: float = 0.0, normalize: bool = True, peak: torch.Tensor | None = None,
-            want_mask: bool = True, out: torch.Tensor | None = None, mask: torch.Tensor | None = None):
+            want_mask: bool = True, out: torch.Tensor | None = None, mask: torch.Tensor | None = None,
+            uniform: bool = False):
     """Recipe K on device-resident packed PCM.
 
     pcm float32 [total], offsets int64 [B], lengths int32 [B] (all CUDA); ``max_length`` is the host's
-    max over lengths.  Returns (input_features float32 [B, T_pad/2, 160], attention_mask int32
-    [B, T_pad/2] or None).
+    max over lengths; ``uniform=True`` promises that every clip has exactly ``max_length`` samples (skips the
+    device-side compaction of work items that ragged batches need).  Returns (input_features float32
+    [B, T_pad/2, 160], attention_mask int32 [B, T_pad/2] or None).
     """
     lib = _lib.load()
     _require_cuda(pcm, "pcm", torch.float32)
@@ -155,7 +157,8 @@ def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max
     _lib.check(lib.stx_fbank_k_workspace(B, int(max_length), C.byref(nbytes)), "stx_fbank_k_workspace")
     ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.stx_fbank_k(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, int(max_length),
+        _lib.check(lib.stx_fbank_k(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B,
+                                   -int(max_length) if uniform else int(max_length),
                                    peak.data_ptr() if peak is not None else None, int(T_pad),
                                    float(padding_value), int(bool(normalize)), out.data_ptr(),
                                    mask.data_ptr() if mask is not None else None, ws.data_ptr(), ws.numel(),

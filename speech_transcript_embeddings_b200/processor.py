@@ -164,7 +164,8 @@ class AudioTextProcessor:
         if self._recipe_k:
             frames = np.array([ops.k_num_frames(int(n)) for n in lengths], dtype=np.int64)
             T_pad, _ = fe._padded_frames(frames, True, None, False, 2)
-            feats, mask = ops.fbank_k(pcm_d, off_d, len_trim, max_len, T_pad, fe.padding_value, True, peak=peak)
+            feats, mask = ops.fbank_k(pcm_d, off_d, len_trim, max_len, T_pad, fe.padding_value, True, peak=peak,
+                                      uniform=bool(lengths.size and lengths.min() == lengths.max()))
         else:
             feats, mask = ops.logmel_w(pcm_d, off_d, len_trim, fe.n_samples, want_mask=fe.return_attention_mask,
                                        peak=peak)

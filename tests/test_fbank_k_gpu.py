@@ -271,3 +271,29 @@ def test_sub_batch_of_clips_shorter_than_a_frame(cuda_device):
     lens = torch.tensor([100, 399], dtype=torch.int32, device=cuda_device)
     x, m = ops.fbank_k(pcm, off, lens, 399, 6, padding_value=1.0)
     assert x.shape == (2, 3, 160) and bool((x == 1.0).all()) and bool((m == 0).all())
+
+
+def test_schedule_and_uniform_promise_give_identical_bits(cuda_device):
+    """Ragged batch: the scheduled work-item list (default), the plain round-robin (`uniform=True`, here a WRONG promise,
+    which may only cost load balance) and the single-group kernel's chunking must produce the same bits -- the statistics
+    are integer sums, so no schedule can change them."""
+    from speech_transcript_embeddings_b200 import ops
+    from speech_transcript_embeddings_b200.feature_extraction import _layout
+    clips = synth.batch_variable(23, seed=77, whole_seconds=False, max_s=12) + [synth.clip("G", 399, 1), synth.clip("U", 400, 2)]
+    lengths = np.array([c.size for c in clips], np.int32)
+    offsets, total = _layout(lengths)
+    host = np.zeros(total, np.float32)
+    for c, o in zip(clips, offsets):
+        host[o:o + c.size] = c
+    pcm = torch.from_numpy(host).to(cuda_device)
+    off = torch.from_numpy(offsets).to(cuda_device)
+    lens = torch.from_numpy(lengths).to(cuda_device)
+    frames = np.array([ops.k_num_frames(int(n)) for n in lengths])
+    T_pad = int(frames.max() + (frames.max() & 1))
+    a, ma = ops.fbank_k(pcm, off, lens, int(lengths.max()), T_pad)
+    b, mb = ops.fbank_k(pcm, off, lens, int(lengths.max()), T_pad, uniform=True)
+    same = (a == b) | (torch.isnan(a) & torch.isnan(b))           # the 400-sample clip has one frame: NaN like NumPy
+    assert bool(same.all()) and torch.equal(ma, mb)
+    ref, _ = OK.extract([clips[3]])
+    T2 = ref.shape[1]
+    assert np.abs(a[3, :T2].cpu().numpy() - ref[0]).max() <= TOL

@@ -62,7 +62,7 @@ if args.recipe == "K":
     masks = [torch.empty((B, T_pad // 2), dtype=torch.int32, device=dev) for _ in range(2)]
 
     def call(i, slot):
-        ops.fbank_k(pcm[i * B * n:(i + 1) * B * n], off, lens, n, T_pad, out=ring[slot], mask=masks[slot])
+        ops.fbank_k(pcm[i * B * n:(i + 1) * B * n], off, lens, n, T_pad, out=ring[slot], mask=masks[slot], uniform=True)
 else:
     ring = [torch.empty((B, 80, 3000), dtype=torch.float32, device=dev) for _ in range(2)]
     masks = None

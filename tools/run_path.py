@@ -31,7 +31,7 @@ ln = torch.full((B,), n, dtype=torch.int32, device=dev)
 for _ in range(iters):
     if recipe == "K":
         T_pad = 2 * ((ops.k_num_frames(n) + 1) // 2)
-        x, m = ops.fbank_k(pcm, off, ln, n, T_pad)
+        x, m = ops.fbank_k(pcm, off, ln, n, T_pad, uniform=True)
     else:
         x, m = ops.logmel_w(pcm, off, ln, n)
 torch.cuda.synchronize()

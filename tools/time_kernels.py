@@ -33,7 +33,7 @@ outs = [torch.empty((B, T_pad // 2, 160) if recipe == "K" else (B, 80, n // 160)
 
 def step(i):
     if recipe == "K":
-        ops.fbank_k(pools[i % 4], off, ln, n, T_pad, out=outs[i % 4])
+        ops.fbank_k(pools[i % 4], off, ln, n, T_pad, out=outs[i % 4], uniform=True)
     else:
         ops.logmel_w(pools[i % 4], off, ln, n, out=outs[i % 4])
 
