@@ -176,6 +176,15 @@ int stx_feature_projection(const float* d_x, const float* d_ln_weight, const flo
                            const float* d_weight, const float* d_bias, int rows, int in_dim, int out_dim,
                            float* d_hidden, float* d_norm, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Retrieval: for every row of A the k (1..8) best-scoring rows of B under the cosine score, WITHOUT
+ * materialising the N x M matrix -- the tensor-core kernel's epilogue keeps the 8 best columns of every 128-column tile in
+ * registers and a merge pass picks the k best of a row.  No counterpart in the reference (its call sites score pairs,
+ * R/inference.py:121, R/cv_inference.py:105); equals sorting stx_cosine_nxm's row by (score descending, column ascending).
+ *   d_val [N, k] float32 scores, d_idx [N, k] int32 row indices of B (-1 where M < k).  Workspace: stx_cosine_topk_workspace. */
+int stx_cosine_topk_workspace(int N, int M, int D, size_t* bytes);
+int stx_cosine_topk(const float* d_a, const float* d_b, int N, int M, int D, int always_normalize, int k, float* d_val,
+                    int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU N x M scoring: this rank's stripe S[rows of a, all M] where the text embeddings b are sharded over
  * `world` ranks of one NVLink/NVSwitch box (BASELINE.json configs[4]).  The reference has no collective; this is the

@@ -158,7 +158,7 @@ c_pos_neg_loss(const float* __restrict__ per_sample, const float* __restrict__ s
 constexpr int kTM = 128, kTN = 128, kTK = 32, kStages = 3;
 constexpr int kTcThreads = 192;
 constexpr int kTileBytes = kTM * kTK * 4;       // one 128 x 32 float plane tile
-constexpr unsigned kTmemCols = 256;             // two 128 x 128 float accumulators
+constexpr unsigned kTmemCols = 512;             // two tiles in flight x two 128 x 128 float accumulators (hi.hi | cross terms)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major A and B,
 // N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr unsigned kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTN >> 3) << 17) | ((unsigned)(kTM >> 4) << 24);
@@ -352,7 +352,12 @@ struct TcGeom {
     const unsigned* flags;          // flags[slot] reaches `epoch` when the slot's planes have landed (nullptr: local data)
     unsigned epoch;
     const float* bias;              // nullptr, or one value per output column added in the epilogue (feature projection)
+    // retrieval mode (top-k): the epilogue does not write S; every (row, column tile) leaves its kTopK best scores and their
+    // column indices (descending; ties: lower column first) in cand_val / cand_idx [row][column tile][kTopK]
+    float* cand_val;
+    int*   cand_idx;
 };
+constexpr int kTopK = 8;            // candidates kept per (row, column tile); stx_cosine_topk serves k <= kTopK
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -432,7 +437,12 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                 const int acc = n & 1;
                 if (n >= 2) mbar_wait(&sm.tmem_empty[acc], (unsigned)(n / 2 - 1) & 1u);     // the epilogue has drained it
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned d = tmem + (unsigned)(acc * kTN);
+                // TWO accumulators per tile: the tensor core truncates (rounds toward zero) after every MMA, which biases a sum of
+                // like-signed products by about -1.8e-8 * D * score when all 3 D / 8 instructions of a tile land on one running
+                // sum (-1.9e-5 at D = 1024, score 1: above the 1e-5 bar exactly for the well-matched pairs the scores are for).
+                // A_hi B_hi carries the magnitude, the two cross products are 2^-11 of it: kept apart, only D / 8 truncations
+                // touch the large sum (bias / 3) and the small one loses nothing that matters; the epilogue adds them in float32.
+                const unsigned d = tmem + (unsigned)(acc * 2 * kTN), dx = d + (unsigned)kTN;
                 for (int kb = 0; kb < kb_per_pass; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&sm.full[s], (unsigned)(it / kStages) & 1u);
@@ -442,8 +452,8 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                         const unsigned long long ah = umma_desc(sm.a_hi[s], k * 32), al = umma_desc(sm.a_lo[s], k * 32);
                         const unsigned long long bh = umma_desc(sm.b_hi[s], k * 32), bl = umma_desc(sm.b_lo[s], k * 32);
                         umma_tf32(d, ah, bh, (kb | k) != 0);
-                        umma_tf32(d, al, bh, 1);
-                        umma_tf32(d, ah, bl, 1);
+                        umma_tf32(dx, al, bh, (kb | k) != 0);
+                        umma_tf32(dx, ah, bl, 1);
                     }
                     umma_commit(&sm.empty[s]);      // the stage is free once these MMAs have read it
                 }
@@ -462,9 +472,14 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
             mbar_wait(&sm.tmem_full[acc], (unsigned)(n / 2) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = ti.m0 + q * 32 + lane;
+            float bv[kTopK];
+            int bi[kTopK];
+#pragma unroll
+            for (int i = 0; i < kTopK; ++i) { bv[i] = __int_as_float(0xff800000); bi[i] = 0x7fffffff; }
 #pragma unroll 1
             for (int c0 = 0; c0 < kTN; c0 += 32) {
-                unsigned r[32];
+                unsigned r[32], rx[32];
+                const unsigned taddr = tmem + ((unsigned)(q * 32) << 16) + (unsigned)(acc * 2 * kTN + c0);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -472,15 +487,43 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
                                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                             : "r"(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(acc * kTN + c0)));
+                             : "r"(taddr));
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(rx[0]), "=r"(rx[1]), "=r"(rx[2]), "=r"(rx[3]), "=r"(rx[4]), "=r"(rx[5]), "=r"(rx[6]), "=r"(rx[7]),
+                               "=r"(rx[8]), "=r"(rx[9]), "=r"(rx[10]), "=r"(rx[11]), "=r"(rx[12]), "=r"(rx[13]), "=r"(rx[14]), "=r"(rx[15]),
+                               "=r"(rx[16]), "=r"(rx[17]), "=r"(rx[18]), "=r"(rx[19]), "=r"(rx[20]), "=r"(rx[21]), "=r"(rx[22]), "=r"(rx[23]),
+                               "=r"(rx[24]), "=r"(rx[25]), "=r"(rx[26]), "=r"(rx[27]), "=r"(rx[28]), "=r"(rx[29]), "=r"(rx[30]), "=r"(rx[31])
+                             : "r"(taddr + (unsigned)kTN));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rx[j]));
                 if (c0 >= ti.n_valid) continue;
                 if (g.bias) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (c0 + j < ti.n_valid) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(g.bias + ti.n0 + c0 + j));
                 }
-                if (row < N) {
+                if (g.cand_val) {
+                    // a score enters the sorted list only if it beats the current k-th best: after the first few columns
+                    // that is rare, so the insertion chain is off the common path
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]);
+                        if (c0 + j < ti.n_valid && v > bv[kTopK - 1]) {
+                            float cv = v;
+                            int ci = ti.n0 + c0 + j;
+#pragma unroll
+                            for (int i = 0; i < kTopK; ++i) {
+                                if (cv > bv[i]) {            // strict: an equal score keeps the earlier (lower) column ahead
+                                    const float tv = bv[i]; const int tix = bi[i];
+                                    bv[i] = cv; bi[i] = ci; cv = tv; ci = tix;
+                                }
+                            }
+                        }
+                    }
+                } else if (row < N) {
                     float* dst = S + (size_t)row * M + ti.n0 + c0;
                     if (vec && (ti.n0 & 3) == 0 && c0 + 32 <= ti.n_valid) {
 #pragma unroll
@@ -494,6 +537,11 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                     }
                 }
             }
+            if (g.cand_val && row < N) {
+                const size_t base = ((size_t)row * n_col_tiles + (size_t)(ti.n0 / kTN)) * kTopK;
+#pragma unroll
+                for (int i = 0; i < kTopK; ++i) { g.cand_val[base + i] = bv[i]; g.cand_idx[base + i] = bi[i]; }
+            }
             // this warp is done with the accumulator: one arrival per epilogue warp frees it for tile n + 2
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -505,6 +553,53 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// Top-k of a row from its per-column-tile candidate lists (c_nxm_tc in retrieval mode).  One warp per row: lane L first
+// merges the lists of tiles L, L + 32, ... into one sorted list of kTopK, then k rounds of a warp-wide arg-max over the
+// lanes' heads (score descending, column ascending on ties) pop the winners in order.
+__device__ __forceinline__ bool topk_before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+__global__ void __launch_bounds__(256)
+c_topk_merge(const float* __restrict__ cand_val, const int* __restrict__ cand_idx, int N, int n_col_tiles, int k,
+             float* __restrict__ out_val, int* __restrict__ out_idx) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= N) return;
+    float lv[kTopK];
+    int li[kTopK];
+#pragma unroll
+    for (int i = 0; i < kTopK; ++i) { lv[i] = __int_as_float(0xff800000); li[i] = 0x7fffffff; }
+    for (int t = lane; t < n_col_tiles; t += 32) {
+        const size_t base = ((size_t)row * n_col_tiles + t) * kTopK;
+#pragma unroll
+        for (int j = 0; j < kTopK; ++j) {
+            float cv = __ldg(cand_val + base + j);
+            int ci = __ldg(cand_idx + base + j);
+#pragma unroll
+            for (int i = 0; i < kTopK; ++i) {
+                if (topk_before(cv, ci, lv[i], li[i])) {
+                    const float tv = lv[i]; const int ti = li[i];
+                    lv[i] = cv; li[i] = ci; cv = tv; ci = ti;
+                }
+            }
+        }
+    }
+    for (int r = 0; r < k; ++r) {
+        float bv = lv[0];
+        int bi = li[0], bl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            if (topk_before(ov, oi, bv, bi) || (ov == bv && oi == bi && ol < bl)) { bv = ov; bi = oi; bl = ol; }
+        }
+        if (lane == 0) { out_val[(size_t)row * k + r] = bv; out_idx[(size_t)row * k + r] = bi == 0x7fffffff ? -1 : bi; }
+        if (lane == bl) {                            // the winner pops its head
+#pragma unroll
+            for (int i = 0; i + 1 < kTopK; ++i) { lv[i] = lv[i + 1]; li[i] = li[i + 1]; }
+            lv[kTopK - 1] = __int_as_float(0xff800000); li[kTopK - 1] = 0x7fffffff;
+        }
     }
 }
 
@@ -628,6 +723,54 @@ int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int 
     g.tiles_start[0] = 0;  g.tiles_start[1] = (M + kTN - 1) / kTN;
     g.slot[0] = 0;  g.m_count[0] = M;  g.col_start[0] = 0;  g.ldS = M;
     return launch_gemm(a_planes, 2 * N, b_planes, 2 * M, Dp, g, g.tiles_start[1], d_S, st);
+}
+
+int stx_cosine_topk_workspace(int N, int M, int D, size_t* bytes) {
+    using namespace stx;
+    size_t base = 0;
+    if (int rc = stx_cosine_workspace(N, M, D, &base)) return rc;
+    const size_t tiles = size_t((M + kTN - 1) / kTN);
+    *bytes = base + align256(size_t(N) * tiles * kTopK * sizeof(float)) + align256(size_t(N) * tiles * kTopK * sizeof(int));
+    return 0;
+}
+
+int stx_cosine_topk(const float* d_a, const float* d_b, int N, int M, int D, int always_normalize, int k, float* d_val,
+                    int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream) {
+    using namespace stx;
+    if (N < 0 || M < 0 || D <= 0) { set_error("stx_cosine_topk: need N, M >= 0, D > 0"); return STX_EINVAL; }
+    if (k < 1 || k > kTopK) { set_error("stx_cosine_topk: k = %d outside 1..%d", k, kTopK); return STX_EINVAL; }
+    if (N == 0) return 0;
+    if (M == 0) { set_error("stx_cosine_topk: M = 0 (nothing to retrieve from)"); return STX_EINVAL; }
+    if (!d_a || !d_b || !d_val || !d_idx || !d_ws) { set_error("stx_cosine_topk: null pointer"); return STX_EINVAL; }
+    if (int rc = check_device()) return rc;
+    size_t need = 0, base = 0;
+    stx_cosine_topk_workspace(N, M, D, &need);
+    stx_cosine_workspace(N, M, D, &base);
+    if (ws_bytes < need) { set_error("stx_cosine_topk: workspace %zu < %zu bytes", ws_bytes, need); return STX_ENOSPACE; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CosWs* ws; float *inv_a, *inv_b;
+    if (int rc = cosine_prepare(d_a, d_b, N, M, D, d_ws, base, st, &ws, &inv_a, &inv_b, !always_normalize)) return rc;
+    const int Dp = padded_d(D);
+    char* p = reinterpret_cast<char*>(inv_b) + align256(size_t(M) * sizeof(float));
+    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(size_t(N) * Dp * sizeof(float));
+    float* b_planes = reinterpret_cast<float*>(p);
+    const int tiles = (M + kTN - 1) / kTN;
+    char* c = static_cast<char*>(d_ws) + base;
+    float* cand_val = reinterpret_cast<float*>(c);  c += align256(size_t(N) * tiles * kTopK * sizeof(float));
+    int* cand_idx = reinterpret_cast<int*>(c);
+    SplitDst dst = {};
+    dst.a_planes = a_planes;  dst.a_plane_stride = size_t(N) * Dp;
+    dst.b_dst[0] = b_planes;  dst.b_plane_stride = size_t(M) * Dp;  dst.n_dst = 1;
+    STX_LAUNCH(c_split, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
+               always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
+    TcGeom g = {};
+    g.n_rows = N;  g.a_plane_rows = N;  g.b_plane_rows = M;  g.world = 1;
+    g.tiles_start[0] = 0;  g.tiles_start[1] = tiles;
+    g.slot[0] = 0;  g.m_count[0] = M;  g.col_start[0] = 0;  g.ldS = M;
+    g.cand_val = cand_val;  g.cand_idx = cand_idx;
+    if (int rc = launch_gemm(a_planes, 2 * N, b_planes, 2 * M, Dp, g, tiles, nullptr, st)) return rc;
+    STX_LAUNCH(c_topk_merge, dim3((N + 7) / 8), dim3(256), 0, st, cand_val, cand_idx, N, tiles, k, d_val, d_idx);
+    return 0;
 }
 
 int stx_score_pos_neg(const float* d_aud, const float* d_pos, const float* d_neg, int B, int D, float temperature,

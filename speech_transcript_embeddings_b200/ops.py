@@ -275,6 +275,28 @@ def cosine_nxm(a: torch.Tensor, b: torch.Tensor, always_normalize: bool = True,
     return out
 
 
+def cosine_topk(a: torch.Tensor, b: torch.Tensor, k: int, always_normalize: bool = True):
+    """For every row of ``a`` the ``k`` (1..8) best rows of ``b`` under the cosine score: (scores float32 [N, k], indices
+    int32 [N, k]), ordered by (score descending, index ascending), without materialising the [N, M] matrix."""
+    lib = _lib.load()
+    _require_cuda(a, "a", torch.float32)
+    _require_cuda(b, "b", torch.float32)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError(f"expected [N, D] and [M, D], got {tuple(a.shape)} and {tuple(b.shape)}")
+    N, D = a.shape
+    M = b.shape[0]
+    val = torch.empty((N, k), dtype=torch.float32, device=a.device)
+    idx = torch.empty((N, k), dtype=torch.int32, device=a.device)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_cosine_topk_workspace(N, M, D, C.byref(nbytes)), "stx_cosine_topk_workspace")
+    ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.stx_cosine_topk(a.data_ptr(), b.data_ptr(), N, M, D, int(bool(always_normalize)), int(k),
+                                       val.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(a.device)),
+                   "stx_cosine_topk")
+    return val, idx
+
+
 def score_pos_neg(aud: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, temperature: float = 0.1,
                   corrupt_gamma: float = 0.35, alignment_factor: torch.Tensor | None = None) -> dict:
     """Evaluation-time scoring of a batch (R/training/trainer_unfreeze.py:1206-1216, 716-741), forward only:

@@ -93,3 +93,46 @@ def test_pos_neg_scoring_consumers(cuda_device):
             loss = per.mean() + (gamma * F.relu(s_neg).mean() if gamma > 0 else 0.0)
             assert abs(float(got["loss"]) - float(loss)) <= 1e-4
             assert (got["hr_pos"].cpu() - torch.sigmoid(s_pos / 0.1)).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("N,M,D,k", [(4096, 4096, 768, 8), (1000, 1003, 100, 5), (130, 3, 64, 8), (7, 1, 32, 1), (300, 129, 1024, 3)])
+def test_topk_equals_sorted_rows_of_the_matrix(cuda_device, N, M, D, k):
+    """Retrieval without the N x M matrix (stx_cosine_topk): bit-identical to sorting stx_cosine_nxm's rows by (score
+    descending, column ascending) -- same kernel, same arithmetic -- and within 1e-5 of the float64 oracle's top-k scores."""
+    from speech_transcript_embeddings_b200 import ops
+    rng = np.random.default_rng(N + M)
+    a = rng.standard_normal((N, D)).astype(np.float32)
+    b = (a[rng.integers(0, N, size=M)] + 0.7 * rng.standard_normal((M, D))).astype(np.float32)
+    ta, tb = torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)
+    val, idx = ops.cosine_topk(ta, tb, k)
+    S = ops.cosine_nxm(ta, tb).cpu().numpy()
+    order = np.lexsort((np.broadcast_to(np.arange(M), S.shape), -S), axis=1)[:, :k]     # score descending, column ascending
+    kk = min(k, M)
+    assert np.array_equal(idx.cpu().numpy()[:, :kk], order[:, :kk])
+    assert np.array_equal(val.cpu().numpy()[:, :kk], np.take_along_axis(S, order[:, :kk], axis=1))
+    if M < k:
+        assert bool((idx[:, M:] == -1).all()) and bool(torch.isinf(val[:, M:]).all())
+    ref = np.sort(OC.matrix_f64(a, b), axis=1)[:, ::-1][:, :kk]
+    assert np.abs(val.cpu().numpy()[:, :kk] - ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("D", [768, 1024])
+def test_matrix_scores_of_well_matched_pairs_hold_the_bar(cuda_device, D):
+    """Scores near 1 are where the tensor core's round-toward-zero accumulation bites: every product has the same sign, so
+    each truncation loses in the same direction (about -1.8e-8 * D * score with one accumulator: -1.9e-5 at D = 1024).  With
+    the A_hi B_hi sum kept apart from the cross terms the worst case stays under the 1e-5 bar (measured 6.4e-6).
+    The seeded cfg5 pairs never exercised this (their cosines are ~0.07)."""
+    from speech_transcript_embeddings_b200 import ops
+    rng = np.random.default_rng(D)
+    a = rng.standard_normal((512, D)).astype(np.float32)
+    worst = 0.0
+    for noise in (0.0, 0.3, 0.7):
+        b = (a + noise * rng.standard_normal((512, D))).astype(np.float32)
+        S = ops.cosine_nxm(torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)).cpu().numpy()
+        ref = OC.matrix_f64(a, b)
+        worst = max(worst, float(np.abs(S - ref).max()))
+        pw = ops.cosine_pairwise(torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device),
+                                 always_normalize=True).cpu().numpy()
+        assert np.abs(np.diag(S) - pw).max() <= 1e-5          # SURVEY 8 a12: the diagonal equals the pairwise scores
+    print(f"D = {D}: worst |S - S_f64| over cos in {{1, 0.96, 0.82}}: {worst:.2e}")
+    assert worst <= 1e-5
