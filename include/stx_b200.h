@@ -110,6 +110,18 @@ int stx_fbank_k_collate(const float* d_pcm, const int64_t* d_offsets, const int3
                         int max_length, int T_pad, float padding_value, float* d_out, int64_t* d_mask,
                         void* d_ws, size_t ws_bytes, void* stream);
 
+/* Recipe K fused with the speech encoder's input stage: raw PCM -> hidden states of
+ * Wav2Vec2BertFeatureProjection = Linear(LayerNorm(input_features)) (TF/models/wav2vec2_bert/modeling_wav2vec2_bert.py:118-130,
+ * called at :1016), [B, T_pad/2, out_dim] float32, without writing and re-reading the normalised features: the CMVN of
+ * stx_fbank_k, the padding, the LayerNorm over the 160 stacked features and the TF32 hi / lo split of the tensor-core
+ * contraction are one pass over the raw log-mel.  d_features (optional) receives exactly what stx_fbank_k would return,
+ * d_mask (optional) its attention mask.  Other arguments as for stx_fbank_k and stx_feature_projection. */
+int stx_fbank_k_projection_workspace(int B, int max_length, int T_pad, int out_dim, int want_features, size_t* bytes);
+int stx_fbank_k_projection(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
+                           const float* d_peak, int T_pad, float padding_value, const float* d_ln_weight,
+                           const float* d_ln_bias, float eps, const float* d_weight, const float* d_bias, int out_dim,
+                           float* d_hidden, float* d_features, int32_t* d_mask, void* d_ws, size_t ws_bytes, void* stream);
+
 /* Per-clip max(1, max|x|) -> d_peak[b] (float32): the divisor of R/processor.py:91-92
  * (division only happens when max|x| > 1; dividing by exactly 1.0f is the identity). */
 int stx_peak_abs(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B,

@@ -655,6 +655,21 @@ int launch_gemm(const float* a_planes, int a_rows_total, const float* b_planes, 
 inline size_t symm_planes_bytes(int world, int m_cap, int Dp) { return align256(size_t(world) * 2 * m_cap * Dp * sizeof(float)); }
 
 }  // namespace
+
+// Linear(in_dim -> out_dim) of rows whose hi / lo TF32 planes are already in a_planes ([2][rows][Dp], Dp = in_dim rounded up
+// to 32): splits the weight into b_planes and runs the tensor-core contraction with the bias epilogue (used by the fused
+// front end, stx_fbank_k_projection in fbank_k.cu; stx_feature_projection above is the same sequence after p_ln_split).
+int project_from_planes(const float* a_planes, int rows, int in_dim, const float* d_weight, const float* d_bias, int out_dim,
+                        float* b_planes, float* d_hidden, cudaStream_t st) {
+    const int Dp = padded_d(in_dim);
+    STX_LAUNCH(p_split, dim3((out_dim + 7) / 8), dim3(256), 0, st, d_weight, out_dim, in_dim, Dp, b_planes, size_t(out_dim) * Dp);
+    TcGeom g = {};
+    g.n_rows = rows;  g.a_plane_rows = rows;  g.b_plane_rows = out_dim;  g.world = 1;
+    g.tiles_start[0] = 0;  g.tiles_start[1] = (out_dim + kTN - 1) / kTN;
+    g.slot[0] = 0;  g.m_count[0] = out_dim;  g.col_start[0] = 0;  g.ldS = out_dim;
+    g.bias = d_bias;
+    return launch_gemm(a_planes, 2 * rows, b_planes, 2 * out_dim, Dp, g, g.tiles_start[1], d_hidden, st);
+}
 }  // namespace stx
 
 extern "C" {

@@ -996,6 +996,81 @@ k_normalize(const int* __restrict__ lengths, const long long* __restrict__ parti
     }
 }
 
+// CMVN + padding + LayerNorm(160) + TF32 hi / lo split in ONE pass over the raw log-mel: the encoder's input stage
+// (Wav2Vec2BertFeatureProjection, TF/models/wav2vec2_bert/modeling_wav2vec2_bert.py:118-130) takes LayerNorm(input_features),
+// so when the caller wants the projected hidden states the normalised features need never be written and re-read
+// (SURVEY.md 8f row 2).  One warp per stacked row (frames 2 j and 2 j + 1 = 160 values, 5 per lane); statistics prologue and
+// CMVN arithmetic exactly as in k_normalize (the optional `feat` output is bit-identical to stx_fbank_k's); raw and feat may
+// be the same buffer.
+__global__ void __launch_bounds__(256)
+k_norm_ln_split(const int* __restrict__ lengths, const long long* __restrict__ partials, int chunk_frames, int chunks_per_clip,
+                int T_pad, float padding_value, const float* raw, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, float* __restrict__ planes, size_t plane_stride,
+                float* feat, int* __restrict__ mask) {
+    __shared__ __align__(16) float s_mean_hi[kMel], s_mean_lo[kMel], s_rstd_f[kMel];
+    __shared__ long long s_sum[kStatWords];
+    const int b = blockIdx.y;
+    const int n = lengths[b];
+    const int T_all = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+    const int T = min(T_all, T_pad);
+    if (T_all > 0) {
+        const int nchunks = (T_all + chunk_frames - 1) / chunk_frames;
+        if (threadIdx.x < kStatWords) {
+            long long acc = 0;
+            const long long* p = partials + (size_t)b * chunks_per_clip * kStatWords + threadIdx.x;
+            for (int c = 0; c < nchunks; ++c) acc += __ldg(p + (size_t)c * kStatWords);
+            s_sum[threadIdx.x] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < kMel) {
+            const int m = threadIdx.x;
+            const double a1 = (double)s_sum[m] * (1.0 / 4294967296.0);
+            const double a2 = (double)s_sum[kMel + m] * (1.0 / 1048576.0) + (double)s_sum[2 * kMel + m] * (1.0 / 72057594037927936.0);
+            const double mean = a1 / (double)T_all;
+            double var = T_all > 1 ? (a2 - a1 * mean) / (double)(T_all - 1) : __longlong_as_double(0x7ff8000000000000LL);
+            if (var < 0.0) var = 0.0;
+            s_mean_hi[m] = (float)mean;
+            s_mean_lo[m] = (float)(mean - (double)(float)mean);
+            s_rstd_f[m] = (float)(1.0 / sqrt(var + 1e-7));
+        }
+    }
+    __syncthreads();
+    const int rows = T_pad / 2;
+    const int lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < rows; j += warps) {
+        const size_t row = (size_t)b * rows + j;
+        const float* src = raw + row * (2 * kMel);
+        float f[5];
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = lane + 32 * k;
+            const int t = 2 * j + (i >= kMel), m = i - (i >= kMel ? kMel : 0);
+            f[k] = t < T ? ((src[i] - s_mean_hi[m]) - s_mean_lo[m]) * s_rstd_f[m] : padding_value;
+            if (feat) feat[row * (2 * kMel) + i] = f[k];
+            sum += f[k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mu = sum * (1.0f / (2 * kMel));
+        float q = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { const float d = f[k] - mu; q = fmaf(d, d, q); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / (2 * kMel)) + eps);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = lane + 32 * k;
+            const float v = (f[k] - mu) * rstd * __ldg(gamma + i) + __ldg(beta + i);
+            const float h = __int_as_float(__float_as_int(v) & 0xffffe000);
+            planes[row * (2 * kMel) + i] = h;
+            planes[plane_stride + row * (2 * kMel) + i] = v - h;
+        }
+        if (mask && lane == 0) mask[row] = (2 * j + 1 < T) ? 1 : 0;
+    }
+}
+
 __global__ void k_peak_init(float* __restrict__ peaks, int B) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) peaks[i] = 1.0f;
@@ -1148,9 +1223,13 @@ int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     return 0;
 }
 
+// What the second pass of a fused consumer needs to know about the first (stx_fbank_k_projection)
+struct FrontInfo { int chunk_frames, chunks, sms; const long long* partials; };
+
 static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
                         const float* d_peak, int T_pad, float padding_value, float tail_value, int normalize,
-                        float* d_out, void* d_mask, int mask_mode, void* d_ws, size_t ws_bytes, void* stream) {
+                        float* d_out, void* d_mask, int mask_mode, void* d_ws, size_t ws_bytes, void* stream,
+                        FrontInfo* info = nullptr) {
     using namespace stx;
     // max_length < 0: the caller promises that EVERY clip has exactly -max_length samples
     const bool uniform = max_length < 0;
@@ -1210,6 +1289,10 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
                        chunk_frames, chunks, d_out, partials);
         }
     }
+    if (info) {
+        info->chunk_frames = chunk_frames; info->chunks = chunks; info->sms = sms; info->partials = partials;
+        return 0;
+    }
     const int quads = T_pad * (kMel / 4);
     // every CTA pays a ~2 us prologue (partials -> mean, 1/std), so the grid is ONE wave of 8 CTAs per SM, not more
     // (cfg2: 64 x 16 CTAs 20.9 us, 64 x 64 CTAs 24.9 us), and never more CTAs than 256-thread groups of float4s
@@ -1231,6 +1314,45 @@ int stx_fbank_k_collate(const float* d_pcm, const int64_t* d_offsets, const int3
                         void* stream) {
     return fbank_k_impl(d_pcm, d_offsets, d_lengths, B, max_length, nullptr, T_pad, padding_value, 0.0f, 1,
                         d_out, d_mask, 1, d_ws, ws_bytes, stream);
+}
+
+int stx_fbank_k_projection_workspace(int B, int max_length, int T_pad, int out_dim, int want_features, size_t* bytes) {
+    using namespace stx;
+    if (B < 0 || T_pad < 0 || (T_pad & 1) || out_dim <= 0 || !bytes) { set_error("stx_fbank_k_projection_workspace: bad argument"); return STX_EINVAL; }
+    size_t front = 0;
+    if (int rc = stx_fbank_k_workspace(B, max_length, &front)) return rc;
+    const size_t rows = size_t(B) * (T_pad / 2);
+    *bytes = front + (want_features ? 0 : align256(rows * 2 * kMel * sizeof(float))) +
+             2 * align256(rows * 2 * kMel * sizeof(float)) + 2 * align256(size_t(out_dim) * 2 * kMel * sizeof(float));
+    return 0;
+}
+
+int stx_fbank_k_projection(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
+                           const float* d_peak, int T_pad, float padding_value, const float* d_ln_weight,
+                           const float* d_ln_bias, float eps, const float* d_weight, const float* d_bias, int out_dim,
+                           float* d_hidden, float* d_features, int32_t* d_mask, void* d_ws, size_t ws_bytes, void* stream) {
+    using namespace stx;
+    if (B < 0 || T_pad < 0 || (T_pad & 1) || out_dim <= 0) { set_error("stx_fbank_k_projection: bad argument"); return STX_EINVAL; }
+    if (B == 0 || T_pad == 0) return 0;
+    if (!d_ln_weight || !d_ln_bias || !d_weight || !d_hidden || !d_ws) { set_error("stx_fbank_k_projection: null pointer"); return STX_EINVAL; }
+    size_t need = 0, front = 0;
+    if (int rc = stx_fbank_k_projection_workspace(B, max_length, T_pad, out_dim, d_features != nullptr, &need)) return rc;
+    if (ws_bytes < need) { set_error("stx_fbank_k_projection: workspace %zu < %zu bytes", ws_bytes, need); return STX_ENOSPACE; }
+    stx_fbank_k_workspace(B, max_length, &front);
+    const size_t rows = size_t(B) * (T_pad / 2);
+    unsigned char* p = static_cast<unsigned char*>(d_ws) + front;
+    float* raw = d_features;
+    if (!raw) { raw = reinterpret_cast<float*>(p); p += align256(rows * 2 * kMel * sizeof(float)); }
+    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(rows * 2 * kMel * sizeof(float));
+    float* b_planes = reinterpret_cast<float*>(p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FrontInfo info = {};
+    if (int rc = fbank_k_impl(d_pcm, d_offsets, d_lengths, B, max_length, d_peak, T_pad, padding_value, padding_value, 1, raw,
+                              nullptr, 0, d_ws, front, stream, &info)) return rc;
+    const int gx = std::max(1, std::min((T_pad / 2 + 7) / 8, std::max(1, (8 * info.sms) / B)));
+    STX_LAUNCH(k_norm_ln_split, dim3(gx, B), dim3(256), 0, st, d_lengths, info.partials, info.chunk_frames, info.chunks, T_pad,
+               padding_value, (const float*)raw, d_ln_weight, d_ln_bias, eps, a_planes, rows * 2 * kMel, d_features, d_mask);
+    return project_from_planes(a_planes, (int)rows, 2 * kMel, d_weight, d_bias, out_dim, b_planes, d_hidden, st);
 }
 
 int stx_peak_abs(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, float* d_peak,

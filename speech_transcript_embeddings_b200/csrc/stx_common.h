@@ -56,4 +56,9 @@ MelCsr build_mel_csr(const std::vector<double>& fb, int nbins, int nmel, double 
 
 int check_device();   // 0 if the current device is sm_100, else STX_EDEVICE
 
+// cosine.cu: Linear over rows whose hi / lo TF32 planes are already written (see there)
+int project_from_planes(const float* a_planes, int rows, int in_dim, const float* d_weight, const float* d_bias, int out_dim,
+                        float* b_planes, float* d_hidden, cudaStream_t st);
+
+
 }  // namespace stx

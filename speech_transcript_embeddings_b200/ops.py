@@ -166,6 +166,47 @@ def fbank_k(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max
     return out, mask
 
 
+def fbank_k_projection(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_length: int, T_pad: int,
+                       ln_weight: torch.Tensor, ln_bias: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None,
+                       eps: float = 1e-5, padding_value: float = 0.0, peak: torch.Tensor | None = None,
+                       want_features: bool = False, want_mask: bool = True, uniform: bool = False):
+    """Recipe K fused with the encoder's input stage: packed PCM -> (hidden float32 [B, T_pad/2, out_dim], input_features
+    [B, T_pad/2, 160] or None, attention_mask int32 [B, T_pad/2] or None).  ``hidden`` is what
+    ``Wav2Vec2BertFeatureProjection`` returns for the extractor's ``input_features`` (LayerNorm(160) + Linear)."""
+    lib = _lib.load()
+    _require_cuda(pcm, "pcm", torch.float32)
+    _require_cuda(offsets, "offsets", torch.int64)
+    _require_cuda(lengths, "lengths", torch.int32)
+    for name, t_ in (("ln_weight", ln_weight), ("ln_bias", ln_bias), ("weight", weight)):
+        _require_cuda(t_, name, torch.float32)
+    if bias is not None:
+        _require_cuda(bias, "bias", torch.float32)
+    if T_pad < 0 or T_pad % 2:
+        raise ValueError("T_pad must be even and >= 0")
+    out_dim = int(weight.shape[0])
+    if tuple(weight.shape) != (out_dim, 2 * K_NMEL) or tuple(ln_weight.shape) != (2 * K_NMEL,) or tuple(ln_bias.shape) != (2 * K_NMEL,):
+        raise ValueError("the projection takes the 160 stacked features: weight [out_dim, 160], LayerNorm parameters [160]")
+    B = lengths.numel()
+    dev = pcm.device
+    hidden = torch.empty((B, T_pad // 2, out_dim), dtype=torch.float32, device=dev)
+    feats = torch.empty((B, T_pad // 2, 2 * K_NMEL), dtype=torch.float32, device=dev) if want_features else None
+    mask = torch.empty((B, T_pad // 2), dtype=torch.int32, device=dev) if want_mask else None
+    ml = -int(max_length) if uniform else int(max_length)
+    nbytes = C.c_size_t(0)
+    _lib.check(lib.stx_fbank_k_projection_workspace(B, ml, int(T_pad), out_dim, int(bool(want_features)), C.byref(nbytes)),
+               "stx_fbank_k_projection_workspace")
+    ws = torch.empty(max(int(nbytes.value), 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.stx_fbank_k_projection(pcm.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), B, ml,
+                                              peak.data_ptr() if peak is not None else None, int(T_pad), float(padding_value),
+                                              ln_weight.data_ptr(), ln_bias.data_ptr(), float(eps), weight.data_ptr(),
+                                              bias.data_ptr() if bias is not None else None, out_dim, hidden.data_ptr(),
+                                              feats.data_ptr() if feats is not None else None,
+                                              mask.data_ptr() if mask is not None else None, ws.data_ptr(), ws.numel(),
+                                              _stream_ptr(dev)), "stx_fbank_k_projection")
+    return hidden, feats, mask
+
+
 def fbank_k_collate(pcm: torch.Tensor, offsets: torch.Tensor, lengths: torch.Tensor, max_length: int, T_pad: int,
                     padding_value: float = 0.0, out: torch.Tensor | None = None, mask: torch.Tensor | None = None):
     """Recipe K with the trainer's collate fused in (R/training/trainer_unfreeze.py:855-866, 898-908):
