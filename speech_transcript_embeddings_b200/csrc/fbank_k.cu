@@ -11,13 +11,20 @@
 // FFT therefore run on the FP64 pipe; everything after the power spectrum is float32 like the
 // reference's own rounding points (complex64 spectrum, float32 log-mel).
 //
-// Two kernels:
-//   k_frames    one CTA per (clip, chunk of frames): PCM -> raw log-mel (written in place into the
-//               output tensor, whose [T_pad/2,160] rows are exactly [T_pad,80] rows) + per-chunk
-//               per-bin (sum, sum of squares) partials in fixed point (int64)
-//   k_normalize every CTA sums its clip's partials (integers: same result in every CTA) -> mean,
-//               1/sqrt(var_ddof1 + 1e-7); then in-place CMVN, padding rows, attention mask (the extractor's int32 mask, or the trainer
-//               collate's int64 mask with zero rows past the clip: R/training/trainer_unfreeze.py:898-908)
+// Kernels:
+//   k_frames_duo  (shipped) persistent, one CTA per SM, two independent 8-warp groups, each streaming through its own list of
+//                 (clip, chunk of frames) work items: PCM -> raw log-mel (written in place into the output tensor, whose
+//                 [T_pad/2,160] rows are exactly [T_pad,80] rows) + per-item per-bin (sum, sum of squares) partials in fixed
+//                 point (int64).  Same phases as k_frames below; the exchange goes through a 64 KB buffer in two halves with
+//                 the second half stashed in tensor memory (see the comment above the kernel)
+//   k_frames      its single-group predecessor, one CTA per (clip, chunk): kept for A/B runs (STX_K_SINGLE=1) and as the
+//                 readable statement of the phases
+//   k_schedule    ragged batches only: compacts the non-empty work items on the device (k_frames_duo is its programmatic
+//                 dependent); skipped when the caller promises a uniform batch (negated max_length)
+//   k_normalize   every CTA sums its clip's partials (integers: same result in every CTA) -> mean, 1/sqrt(var_ddof1 + 1e-7);
+//                 then in-place CMVN, padding rows, attention mask (the extractor's int32 mask, or the trainer collate's int64
+//                 mask with zero rows past the clip: R/training/trainer_unfreeze.py:898-908)
+//   k_norm_ln_split  k_normalize fused with the encoder's LayerNorm + TF32 split (stx_fbank_k_projection)
 //
 // k_frames keeps ONE FRAME PER LANE: a tile is 32 consecutive frames of a clip and the 16 warps of the
 // CTA split each frame's 512-point real FFT (n = 16 n1 + n2, k = k1 + 32 k2) between them, so every
