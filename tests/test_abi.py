@@ -51,3 +51,29 @@ def test_no_silent_cpu_path():
         ops.cosine_pairwise(x.view(1, -1), x.view(1, -1))
     with pytest.raises(_lib.StxError):
         B200SeamlessM4TFeatureExtractor()(np.zeros(1000, np.float32), sampling_rate=16000)
+
+
+def test_argument_errors_of_the_newer_entry_points(lib):
+    """Argument checks run before any device work, so they can be exercised without a GPU."""
+    n = C.c_size_t(0)
+    assert lib.stx_cosine_topk(None, None, 4, 4, 8, 1, 0, None, None, None, 0, None) == -1          # k outside 1..8
+    assert b"outside 1..8" in lib.stx_last_error()
+    assert lib.stx_cosine_topk(None, None, 4, 4, 8, 1, 9, None, None, None, 0, None) == -1
+    assert lib.stx_cosine_topk(None, None, 4, 4, 8, 1, 3, None, None, None, 0, None) == -1          # null pointers
+    assert lib.stx_cosine_topk_workspace(4096, 4096, 768, C.byref(n)) == 0 and n.value > 4096 * 32 * 8 * 8
+    assert lib.stx_resample_poly(None, None, None, 1, 16000, 16000, None, None, None, 0, None, None) == -1
+    assert lib.stx_resample_poly(None, None, None, 1, 48000, 16000, None, None, None, 0, None, None) == -1
+    assert b"null pointer" in lib.stx_last_error()
+    assert lib.stx_resample_plan(0, 16000, None, None, None, None, None) == -1
+    up, down, taps = C.c_int(0), C.c_int(0), C.c_int(0)
+    assert lib.stx_resample_plan(44100, 16000, C.byref(up), C.byref(down), C.byref(taps), None, None) == 0
+    assert (up.value, down.value, taps.value) == (160, 441, 58)
+    assert lib.stx_fbank_k_projection_workspace(4, 480000, 3, 1024, 0, C.byref(n)) == -1            # odd T_pad
+    assert lib.stx_fbank_k_projection_workspace(4, 480000, 3000, 1024, 0, C.byref(n)) == 0 and n.value > 4 * 1500 * 160 * 4 * 3
+    assert lib.stx_fbank_k_projection(None, None, None, 4, 480000, None, 3000, 0.0, None, None, 1e-5, None, None, 1024,
+                                      None, None, None, None, 0, None) == -1
+    assert b"null pointer" in lib.stx_last_error()
+    # the "uniform batch" promise is a negated max_length: sizes are those of |max_length|
+    a, b = C.c_size_t(0), C.c_size_t(0)
+    assert lib.stx_fbank_k_workspace(8, 480000, C.byref(a)) == 0 and lib.stx_fbank_k_workspace(8, -480000, C.byref(b)) == 0
+    assert a.value == b.value
