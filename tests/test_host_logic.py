@@ -120,3 +120,36 @@ def test_load_audio_reads_pcm_wav_without_librosa(tmp_path):
     bad.write_bytes(b"ID3\x03" + bytes(64))
     with pytest.raises(ImportError):
         load_audio(bad)
+
+
+@pytest.mark.parametrize("width", [1, 2, 3, 4])
+def test_load_audio_pcm_widths(tmp_path, width):
+    """8/16/24/32-bit PCM WAV with libsndfile's scaling (full scale = 1.0); mono stays mono."""
+    import wave
+    from speech_transcript_embeddings_b200.processor import load_audio
+    try:
+        import librosa  # noqa: F401
+        pytest.skip("librosa installed: the reference's own decoder is used")
+    except ImportError:
+        pass
+    rng = np.random.default_rng(width)
+    n = 1000
+    if width == 1:
+        v = rng.integers(0, 256, size=n)
+        raw, want = v.astype(np.uint8).tobytes(), (v.astype(np.float32) - 128.0) / 128.0
+    elif width == 2:
+        v = rng.integers(-32768, 32768, size=n)
+        raw, want = v.astype("<i2").tobytes(), v.astype(np.float32) / 32768.0
+    elif width == 3:
+        v = rng.integers(-(1 << 23), 1 << 23, size=n)
+        raw = b"".join(int(x & 0xFFFFFF).to_bytes(3, "little") for x in v)
+        want = v.astype(np.float32) / 8388608.0
+    else:
+        v = rng.integers(-(1 << 31), 1 << 31, size=n)
+        raw, want = v.astype("<i4").tobytes(), (v.astype(np.float64) / 2147483648.0).astype(np.float32)
+    path = tmp_path / f"w{width}.wav"
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(width); w.setframerate(22050)
+        w.writeframes(raw)
+    x, sr = load_audio(path)
+    assert sr == 22050 and x.dtype == np.float32 and np.array_equal(x, want)
