@@ -50,11 +50,34 @@
 //            metadata decode) -> ln -> staged rows -> coalesced stores + float64 sum / sum of squares per bin
 #include "stx_common.h"
 #include "codelets.cuh"
+#include "mel_k.cuh"
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
 #include <mutex>
+
+// Build-time switches for A/B runs (tools/ab_build.py); the defaults are the shipped configuration.
+#ifndef STX_K_MEL_GEN
+#define STX_K_MEL_GEN 0          // mel stage of k_frames_duo (cfg2, us per launch of k_frames_duo, profiles/r02_k_variants.md):
+                                 // 0: filter-walking, weights and first bins in shared memory (round 1)            217.3
+                                 // 1: generated bin-walking stage (mel_k.cuh): a third of the shared-memory reads and 8 % fewer
+                                 //    instructions, but eight divergent code paths per group -- instruction-fetch stalls go
+                                 //    from 0.13 to 1.01 per issue                                                  236.8
+                                 // 2: filter-walking with the (warp-uniform) weights in the constant bank: 430 fewer
+                                 //    shared-memory wavefronts per tile, 54 more uniform loads                      220.7
+#endif
+#ifndef STX_K_CLIPSTATS
+#define STX_K_CLIPSTATS 0        // 1: the group that completes a clip's last work item (atomic counter per clip) reduces the clip's
+                                 //    statistics inside k_frames_duo, so that k_normalize starts streaming at once: k_normalize
+                                 //    23.0 -> 20.8 us, but k_frames_duo 220.7 -> 236.2 us (a fence, two group barriers and an L2
+                                 //    atomic per work item sit on the group's critical path).  0: every CTA of k_normalize sums the
+                                 //    clip's partials itself (round 1)
+#endif
+#ifndef STX_K_NORM_PDL
+#define STX_K_NORM_PDL 0         // 1: k_normalize is launched as the programmatic dependent of k_frames_duo (no measurable gain:
+                                 //    the frames kernel owns every SM until its last CTA retires)
+#endif
 
 namespace stx {
 namespace {
@@ -201,6 +224,27 @@ __device__ __forceinline__ StageRange stage_range(int s0, int n, bool aligned) {
     return r;
 }
 
+__constant__ __align__(16) float c_melw[kMelWeights];     // [slot][warp][mel_len(slot)]
+__constant__ int c_melfirst[kMel];
+
+// Filter-walking mel slot with warp-uniform weights from the constant bank: only the power spectrum goes through the
+// shared-memory pipe (704 reads per frame instead of 704 + 176 + 80)
+template <int kSlot>
+__device__ __forceinline__ float mel_slot_c(const float* __restrict__ Pl, int warp) {
+    constexpr int L = mel_len(kSlot);
+    const float* pk = Pl + c_melfirst[16 * kSlot + warp] * kTile;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(&c_melw[mel_off(kSlot) + warp * L + 4 * q]);
+        acc0 = fmaf(w.x, pk[(4 * q + 0) * kTile], acc0);
+        acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
+        acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
+        acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
+    }
+    return ln_pos(fmaxf(acc0 + acc1, kMelFloor));
+}
+
 template <int kSlot>
 __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const float* __restrict__ melw,
                                           const int* __restrict__ melfirst, int warp) {
@@ -230,7 +274,7 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
     const int b = blockIdx.y;
     const int chunk = blockIdx.x;
     const int n = lengths[b];
-    const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+    const int T = min(n >= kFrame ? 1 + (n - kFrame) / kHop : 0, chunks_per_clip * chunk_frames);
     const int t_begin = chunk * chunk_frames;
     if (t_begin >= T) return;                       // uniform per CTA
     const int t_end = min(T, t_begin + chunk_frames);
@@ -494,6 +538,7 @@ struct TileDesc {
     int n, t0, t_end, item;
     float peak;
     int aligned, valid, last;    // last: the item ends with this tile (flush the statistics)
+    int b, nitems;               // clip index and the number of work items of that clip
 };
 struct SmemG {
     double2 ex[8][16][kTile];    // one HALF of the exchange: [slot][n2][lane].  H1: slot 0 = (row 0, row 16) (both real), slots
@@ -508,6 +553,7 @@ struct SmemG {
     unsigned long long mbar;     // TMA completion
     unsigned long long cbar;     // cval ready (one arrival per warp of the group)
     TileDesc desc[2];            // the tile in flight and the next one (written by the group's thread 0)
+    int is_last;                 // this group completed the last work item of a clip (it reduces the clip's statistics)
 };
 struct SmemDuo {
     SmemG g[2];
@@ -548,11 +594,27 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
 }
 
+// mean and 1/sqrt(var + 1e-7) of one mel bin from the clip's fixed-point sums (sum x on the 2^-32 grid, sum x^2 as a 2^-20-grid
+// part plus a 2^-56-grid remainder); var with ddof = 1 (…seamless_m4t.py:257-262).  The mean is returned as two float32
+// words (k_normalize subtracts both).  A single frame has no ddof=1 variance: numpy returns NaN there and so do we.
+__device__ __forceinline__ void clip_stats(long long s1, long long s2h, long long s2l, int T_all, float& mean_hi, float& mean_lo,
+                                           float& rstd) {
+    const double a1 = (double)s1 * (1.0 / 4294967296.0);
+    const double a2 = (double)s2h * (1.0 / 1048576.0) + (double)s2l * (1.0 / 72057594037927936.0);
+    const double mean = a1 / (double)T_all;
+    double var = T_all > 1 ? (a2 - a1 * mean) / (double)(T_all - 1) : __longlong_as_double(0x7ff8000000000000LL);
+    if (var < 0.0) var = 0.0;                                  // rounding of a constant column; keeps NaN
+    mean_hi = (float)mean;
+    mean_lo = (float)(mean - (double)(float)mean);
+    rstd = (float)(1.0 / sqrt(var + 1e-7));
+}
+
 template <bool kPeak>
 __global__ void __launch_bounds__(kThreads, 1)
 k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
              const float* __restrict__ peaks, const KTables* __restrict__ tab, int B, int T_pad, int chunk_frames,
-             int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials, const int* __restrict__ sched) {
+             int chunks_per_clip, float* __restrict__ out, long long* __restrict__ partials, const int* __restrict__ sched,
+             unsigned* __restrict__ done, float* __restrict__ cstat) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemDuo& sm = *reinterpret_cast<SmemDuo*>(smem_raw);
 
@@ -585,7 +647,8 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             const int item = sched ? __ldg(sched + 1 + pos) : pos;
             const int b = item / chunks_per_clip, chunk = item - b * chunks_per_clip;
             const int n = __ldg(lengths + b);
-            const int T = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+            // (a clip longer than the max_length the caller sized the call for is processed up to that length)
+            const int T = min(n >= kFrame ? 1 + (n - kFrame) / kHop : 0, chunks_per_clip * chunk_frames);
             const int t_begin = chunk * chunk_frames;
             if (t_begin >= T) continue;              // (only without a schedule, and only if the caller's promise was wrong)
             d.valid = 1; d.item = pos; d.n = n; d.t0 = t_begin; d.t_end = min(T, t_begin + chunk_frames);
@@ -594,6 +657,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             d.peak = kPeak ? __ldg(peaks + b) : 1.0f;
             d.out_b = out + (size_t)b * T_pad * kMel;
             d.part = partials + (size_t)item * kStatWords;
+            d.b = b; d.nitems = (T + chunk_frames - 1) / chunk_frames;
             break;
         }
     };
@@ -621,12 +685,19 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+#if STX_K_MEL_GEN == 0
     for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
     if (tid < kMel) sm.melfirst[tid] = tab->melfirst[tid];
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                                // mbarrier init, tables, TMEM base visible
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");      // the schedule (k_schedule, the programmatic primary, if any) is complete
+#if STX_K_NORM_PDL
+    // k_normalize (the programmatic dependent) may be scheduled onto SMs as they drain; its CTAs block in griddepcontrol.wait
+    // until this whole grid has completed and flushed, so only its launch latency is hidden
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     if (tl == 0) {
         open_item(2 * blockIdx.x + g, sg.desc[0]);
         prefetch(sg.desc[0]);
@@ -739,7 +810,9 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             if (r == 0) sg.cval[fr] = (v - sg.xb[fr]) * (1.0 / 400.0);
+#if STX_K_MEL_GEN != 1
             if (w8 == 1) sg.u.P[0][lane] = 0.0f;     // padded mel filters may touch bin 0 with a zero weight
+#endif
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sg.cbar)) : "memory");
         }
@@ -807,10 +880,25 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         group_bar(g);                               // power spectrum complete; the exchange buffer is idle until the next pass 1
         if (tl == 0) prefetch(sg.desc[slot ^ 1]);   // ... and takes the next tile's PCM meanwhile
 
-        // ---- sparse mel + ln: warp w8 owns the mel bins of roles w8 and w8 + 8 ----
+        // ---- sparse mel + ln ----
         {
             const float* Pl = &sg.u.P[0][lane];
             float* orow = outstage + lane * kOutRow;
+#if STX_K_MEL_GEN == 1
+            // warp w8 owns a contiguous range of filters and reads every bin they touch ONCE; weights are immediates
+            // (generated: mel_k.cuh).  281 shared-memory reads per frame instead of 704 + 176 + 80.
+            melk::mel_rows_dispatch(w8, Pl, orow, [](float a) { return ln_pos(fmaxf(a, kMelFloor)); });
+#elif STX_K_MEL_GEN == 2
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int wr = w8 + h * kGWarps;
+                orow[wr]      = mel_slot_c<0>(Pl, wr);
+                orow[wr + 16] = mel_slot_c<1>(Pl, wr);
+                orow[wr + 32] = mel_slot_c<2>(Pl, wr);
+                orow[wr + 48] = mel_slot_c<3>(Pl, wr);
+                orow[wr + 64] = mel_slot_c<4>(Pl, wr);
+            }
+#else
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int wr = w8 + h * kGWarps;
@@ -820,6 +908,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 orow[wr + 48] = mel_slot<3>(Pl, sm.melw, sm.melfirst, wr);
                 orow[wr + 64] = mel_slot<4>(Pl, sm.melw, sm.melfirst, wr);
             }
+#endif
         }
         group_bar(g);
 
@@ -854,6 +943,47 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 cur.part[tl] = (long long)(red[which * kGStat + m] + red[which * kGStat + kMel + m] + red[which * kGStat + 2 * kMel + m]);
             }
             s1 = 0; s2h = 0; s2l = 0;
+#if STX_K_CLIPSTATS
+            if (cstat) {
+                // ---- count the item; the group that completes the clip reduces its statistics (integer sums of the items'
+                // partials: the same bits whichever group does it) and leaves mean / 1/std per bin for k_normalize ----
+                __threadfence();                     // this item's partials are visible device-wide before it is counted
+                group_bar(g);
+                if (tl == 0) {
+                    const unsigned old = atomicAdd(done + cur.b, 1u);
+                    const int last = (old + 1u == (unsigned)cur.nitems);
+                    if (last) done[cur.b] = 0u;      // self-cleaning: the counters are zero again when the kernel ends
+                    sg.is_last = last;
+                }
+                group_bar(g);
+                if (sg.is_last) {
+                    __threadfence();
+                    if (tl < kStatWords) {
+                        const long long* p = partials + (size_t)cur.b * chunks_per_clip * kStatWords + tl;
+                        const int nit = cur.nitems;
+                        long long acc = 0;
+                        int c = 0;
+                        for (; c + 8 <= nit; c += 8) {                       // 8 independent L2 loads in flight
+                            long long v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + (size_t)(c + u) * kStatWords);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc += v[u];
+                        }
+                        for (; c < nit; ++c) acc += __ldcg(p + (size_t)c * kStatWords);
+                        red[tl] = (unsigned long long)acc;
+                    }
+                    group_bar(g);
+                    if (tl < kMel) {
+                        const int T_all = min(1 + (cur.n - kFrame) / kHop, chunks_per_clip * chunk_frames);
+                        float mh, ml, rs;
+                        clip_stats((long long)red[tl], (long long)red[kMel + tl], (long long)red[2 * kMel + tl], T_all, mh, ml, rs);
+                        float* cs = cstat + (size_t)cur.b * kStatWords;
+                        cs[tl] = mh; cs[kMel + tl] = ml; cs[2 * kMel + tl] = rs;
+                    }
+                }
+            }
+#endif
         }
         slot ^= 1;
       }
@@ -929,18 +1059,31 @@ k_schedule(const int* __restrict__ lengths, int B, int chunk_frames, int chunks_
 __global__ void __launch_bounds__(256)
 k_normalize(const int* __restrict__ lengths, const long long* __restrict__ partials, int chunk_frames, int chunks_per_clip,
             int T_pad, float padding_value, float tail_value, int normalize, float* __restrict__ out,
-            void* __restrict__ mask, int mask_mode) {
+            void* __restrict__ mask, int mask_mode, const float* __restrict__ cstat) {
     __shared__ __align__(16) float s_mean_hi[kMel], s_mean_lo[kMel], s_rstd_f[kMel];
     __shared__ long long s_sum[kStatWords];
     const int b = blockIdx.y;
     const int n = lengths[b];
-    const int T_all = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;      // the statistics are over ALL frames of the clip
+#if STX_K_NORM_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // k_frames_duo (the programmatic primary) has completed
+#endif
+    // the statistics are over ALL frames of the clip (all that were processed: a clip longer than the max_length the call was
+    // sized for is cut there, in every kernel alike)
+    const int T_all = min(n >= kFrame ? 1 + (n - kFrame) / kHop : 0, chunks_per_clip * chunk_frames);
     const int T = min(T_all, T_pad);
     const int T2 = min((T + 1) & ~1, T_pad);
     // mean and 1/sqrt(var + 1e-7) per bin, var with ddof = 1 (…seamless_m4t.py:257-262): integer sums of the chunk
     // partials are exact and order-independent, so every CTA of the clip (and every batch) gets the same bits
-    if (normalize && T_all > 0) {
-        const int nchunks = (T_all + chunk_frames - 1) / chunk_frames;
+    if (normalize && T_all > 0 && cstat) {
+        // the statistics were reduced inside k_frames_duo by the group that completed the clip
+        if (threadIdx.x < kMel) {
+            const float* cs = cstat + (size_t)b * kStatWords;
+            s_mean_hi[threadIdx.x] = cs[threadIdx.x];
+            s_mean_lo[threadIdx.x] = cs[kMel + threadIdx.x];
+            s_rstd_f[threadIdx.x] = cs[2 * kMel + threadIdx.x];
+        }
+    } else if (normalize && T_all > 0) {
+        const int nchunks = min((T_all + chunk_frames - 1) / chunk_frames, chunks_per_clip);
         if (threadIdx.x < kStatWords) {
             long long acc = 0;
             const long long* p = partials + (size_t)b * chunks_per_clip * kStatWords + threadIdx.x;
@@ -958,15 +1101,7 @@ k_normalize(const int* __restrict__ lengths, const long long* __restrict__ parti
         __syncthreads();
         if (threadIdx.x < kMel) {
             const int m = threadIdx.x;
-            const double a1 = (double)s_sum[m] * (1.0 / 4294967296.0);
-            const double a2 = (double)s_sum[kMel + m] * (1.0 / 1048576.0) + (double)s_sum[2 * kMel + m] * (1.0 / 72057594037927936.0);
-            const double mean = a1 / (double)T_all;
-            // a single frame has no ddof=1 variance: numpy returns NaN there and so do we
-            double var = T_all > 1 ? (a2 - a1 * mean) / (double)(T_all - 1) : __longlong_as_double(0x7ff8000000000000LL);
-            if (var < 0.0) var = 0.0;                                  // rounding of a constant column; keeps NaN
-            s_mean_hi[m] = (float)mean;
-            s_mean_lo[m] = (float)(mean - (double)(float)mean);
-            s_rstd_f[m] = (float)(1.0 / sqrt(var + 1e-7));
+            clip_stats(s_sum[m], s_sum[kMel + m], s_sum[2 * kMel + m], T_all, s_mean_hi[m], s_mean_lo[m], s_rstd_f[m]);
         }
     }
     __syncthreads();
@@ -1013,14 +1148,21 @@ __global__ void __launch_bounds__(256)
 k_norm_ln_split(const int* __restrict__ lengths, const long long* __restrict__ partials, int chunk_frames, int chunks_per_clip,
                 int T_pad, float padding_value, const float* raw, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float eps, float* __restrict__ planes, size_t plane_stride,
-                float* feat, int* __restrict__ mask) {
+                float* feat, int* __restrict__ mask, const float* __restrict__ cstat) {
     __shared__ __align__(16) float s_mean_hi[kMel], s_mean_lo[kMel], s_rstd_f[kMel];
     __shared__ long long s_sum[kStatWords];
     const int b = blockIdx.y;
     const int n = lengths[b];
-    const int T_all = n >= kFrame ? 1 + (n - kFrame) / kHop : 0;
+    const int T_all = min(n >= kFrame ? 1 + (n - kFrame) / kHop : 0, chunks_per_clip * chunk_frames);
     const int T = min(T_all, T_pad);
-    if (T_all > 0) {
+    if (T_all > 0 && cstat) {
+        if (threadIdx.x < kMel) {
+            const float* cs = cstat + (size_t)b * kStatWords;
+            s_mean_hi[threadIdx.x] = cs[threadIdx.x];
+            s_mean_lo[threadIdx.x] = cs[kMel + threadIdx.x];
+            s_rstd_f[threadIdx.x] = cs[2 * kMel + threadIdx.x];
+        }
+    } else if (T_all > 0) {
         const int nchunks = (T_all + chunk_frames - 1) / chunk_frames;
         if (threadIdx.x < kStatWords) {
             long long acc = 0;
@@ -1031,14 +1173,7 @@ k_norm_ln_split(const int* __restrict__ lengths, const long long* __restrict__ p
         __syncthreads();
         if (threadIdx.x < kMel) {
             const int m = threadIdx.x;
-            const double a1 = (double)s_sum[m] * (1.0 / 4294967296.0);
-            const double a2 = (double)s_sum[kMel + m] * (1.0 / 1048576.0) + (double)s_sum[2 * kMel + m] * (1.0 / 72057594037927936.0);
-            const double mean = a1 / (double)T_all;
-            double var = T_all > 1 ? (a2 - a1 * mean) / (double)(T_all - 1) : __longlong_as_double(0x7ff8000000000000LL);
-            if (var < 0.0) var = 0.0;
-            s_mean_hi[m] = (float)mean;
-            s_mean_lo[m] = (float)(mean - (double)(float)mean);
-            s_rstd_f[m] = (float)(1.0 / sqrt(var + 1e-7));
+            clip_stats(s_sum[m], s_sum[kMel + m], s_sum[2 * kMel + m], T_all, s_mean_hi[m], s_mean_lo[m], s_rstd_f[m]);
         }
     }
     __syncthreads();
@@ -1149,6 +1284,20 @@ int get_tables(const KTables** out) {
             h.melfirst[m] = lo;
             for (int q = 0; q < L; ++q) h.melw[mel_off(slot) + wrp * L + q] = float(fb[size_t(lo + q) * kMel + m]);
         }
+        // the generated mel stage (mel_k.cuh) carries its weights as immediates: they must be this library's table
+        {
+            int at = 0;
+            for (int m = 0; m < kMel; ++m) {
+                int lo = -1, hi = -1;
+                for (int k = 0; k <= STX_K_NFFT / 2; ++k)
+                    if (fb[size_t(k) * kMel + m] != 0.0) { if (lo < 0) lo = k; hi = k; }
+                if (lo != melk::kMelFirstBin[m] || hi != melk::kMelLastBin[m]) { set_error("mel_k.cuh: filter %d spans bins %d..%d, the table says %d..%d (rerun tools/gen_mel_k.py)", m, melk::kMelFirstBin[m], melk::kMelLastBin[m], lo, hi); return STX_EINVAL; }
+                for (int k = lo; k <= hi; ++k, ++at)
+                    if (melk::kMelWeightsFlat[at] != float(fb[size_t(k) * kMel + m])) { set_error("mel_k.cuh: weight of filter %d at bin %d differs from the table (rerun tools/gen_mel_k.py)", m, k); return STX_EINVAL; }
+            }
+        }
+        STX_CUDA(cudaMemcpyToSymbol(c_melw, h.melw, sizeof(h.melw)));
+        STX_CUDA(cudaMemcpyToSymbol(c_melfirst, h.melfirst, sizeof(h.melfirst)));
         KTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(KTables)));
         STX_CUDA(cudaMemcpy(d, &h, sizeof(KTables), cudaMemcpyHostToDevice));
@@ -1208,6 +1357,25 @@ int launch_dependent(const char* name, K kernel, dim3 grid, dim3 block, size_t s
     if (e != cudaSuccess) return cuda_fail(e, name);
     return 0;
 }
+// Per (device, stream) completion counters of k_frames_duo (one per clip).  They are zero whenever no call is in flight on
+// the stream: allocated and zeroed once, and the kernel resets every counter it has driven to its final value (calls on one
+// stream are serialised, so one set per stream is enough; the memory is never freed, 256 KB per stream that ever ran recipe K).
+constexpr int kMaxClips = 65536;
+std::mutex g_state_mutex;
+std::vector<std::pair<std::pair<int, cudaStream_t>, unsigned*>> g_state;
+int get_counters(cudaStream_t st, unsigned** out) {
+    int dev = 0;
+    STX_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_state_mutex);
+    for (auto& e : g_state)
+        if (e.first.first == dev && e.first.second == st) { *out = e.second; return 0; }
+    unsigned* p = nullptr;
+    STX_CUDA(cudaMalloc(&p, sizeof(unsigned) * kMaxClips));
+    STX_CUDA(cudaMemsetAsync(p, 0, sizeof(unsigned) * kMaxClips, st));
+    g_state.push_back({{dev, st}, p});
+    *out = p;
+    return 0;
+}
 inline bool use_duo() {
     static const bool v = [] { const char* e = std::getenv("STX_K_SINGLE"); return !(e && e[0] == '1'); }();
     return v;
@@ -1224,14 +1392,16 @@ int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     if (B < 0 || max_length == INT32_MIN || !bytes) { set_error("stx_fbank_k_workspace: bad argument"); return STX_EINVAL; }
     if (max_length < 0) max_length = -max_length;          // the "uniform batch" form of stx_fbank_k
     const int chunks = (frames_of(max_length) + kMinChunk - 1) / kMinChunk;
-    // per-chunk statistics partials, then the schedule of k_frames_duo (item count + one int per item)
+    // per-chunk statistics partials, then the schedule of k_frames_duo (item count + one int per item), then the per-clip
+    // statistics (mean hi / lo, 1/std per bin)
     *bytes = align256(size_t(B) * std::max(chunks, 1) * kStatWords * sizeof(long long)) +
-             align256(sizeof(int) * (1 + size_t(B) * std::max(chunks, 1)));
+             align256(sizeof(int) * (1 + size_t(B) * std::max(chunks, 1))) +
+             align256(size_t(B) * kStatWords * sizeof(float));
     return 0;
 }
 
 // What the second pass of a fused consumer needs to know about the first (stx_fbank_k_projection)
-struct FrontInfo { int chunk_frames, chunks, sms; const long long* partials; };
+struct FrontInfo { int chunk_frames, chunks, sms; const long long* partials; const float* cstat; };
 
 static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_lengths, int B, int max_length,
                         const float* d_peak, int T_pad, float padding_value, float tail_value, int normalize,
@@ -1271,6 +1441,14 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
     long long* partials = static_cast<long long*>(d_ws);
     const int chunks64 = std::max((frames_of(max_length) + kMinChunk - 1) / kMinChunk, 1);
     int* sched = reinterpret_cast<int*>(static_cast<unsigned char*>(d_ws) + align256(size_t(B) * chunks64 * kStatWords * sizeof(long long)));
+    float* cstat = nullptr;
+    unsigned* done = nullptr;
+#if STX_K_CLIPSTATS
+    if (duo && normalize && frames_of(max_length) > 0) {
+        cstat = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sched) + align256(sizeof(int) * (1 + size_t(B) * chunks64)));
+        if (int rc = get_counters(st, &done)) return rc;
+    }
+#endif
     if (frames_of(max_length) > 0) {
         const int duo_grid = (int)std::min<long long>(sms, ((long long)B * chunks + 1) / 2);
         // uniform batch (the caller's promise): no empty items, the plain round-robin is balanced, and the 3.6 us of
@@ -1282,9 +1460,9 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
             const long long* off = reinterpret_cast<const long long*>(d_offsets);
             const int rc = d_peak
                 ? launch_dependent("k_frames_duo<true>", k_frames_duo<true>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
-                                   d_pcm, off, d_lengths, d_peak, tab, B, T_pad, chunk_frames, chunks, d_out, partials, sched_arg)
+                                   d_pcm, off, d_lengths, d_peak, tab, B, T_pad, chunk_frames, chunks, d_out, partials, sched_arg, done, cstat)
                 : launch_dependent("k_frames_duo<false>", k_frames_duo<false>, dim3(duo_grid), dim3(kThreads), sizeof(SmemDuo), st,
-                                   d_pcm, off, d_lengths, d_peak, tab, B, T_pad, chunk_frames, chunks, d_out, partials, sched_arg);
+                                   d_pcm, off, d_lengths, d_peak, tab, B, T_pad, chunk_frames, chunks, d_out, partials, sched_arg, done, cstat);
             if (rc) return rc;
         } else if (d_peak) {
             STX_LAUNCH(k_frames<true>, dim3(chunks, B), dim3(kThreads), sizeof(Smem), st,
@@ -1297,15 +1475,21 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
         }
     }
     if (info) {
-        info->chunk_frames = chunk_frames; info->chunks = chunks; info->sms = sms; info->partials = partials;
+        info->chunk_frames = chunk_frames; info->chunks = chunks; info->sms = sms; info->partials = partials; info->cstat = cstat;
         return 0;
     }
     const int quads = T_pad * (kMel / 4);
     // every CTA pays a ~2 us prologue (partials -> mean, 1/std), so the grid is ONE wave of 8 CTAs per SM, not more
     // (cfg2: 64 x 16 CTAs 20.9 us, 64 x 64 CTAs 24.9 us), and never more CTAs than 256-thread groups of float4s
     const int gx = std::max(1, std::min((quads + 255) / 256, std::max(1, (8 * sms) / B)));
+#if STX_K_NORM_PDL
+    if (duo)
+        return launch_dependent("k_normalize", k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, (const long long*)partials,
+                                chunk_frames, chunks, T_pad, padding_value, tail_value, normalize, d_out, d_mask, mask_mode,
+                                (const float*)cstat);
+#endif
     STX_LAUNCH(k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, partials, chunk_frames, chunks, T_pad, padding_value,
-               tail_value, normalize, d_out, d_mask, mask_mode);
+               tail_value, normalize, d_out, d_mask, mask_mode, (const float*)cstat);
     return 0;
 }
 
@@ -1358,7 +1542,8 @@ int stx_fbank_k_projection(const float* d_pcm, const int64_t* d_offsets, const i
                               nullptr, 0, d_ws, front, stream, &info)) return rc;
     const int gx = std::max(1, std::min((T_pad / 2 + 7) / 8, std::max(1, (8 * info.sms) / B)));
     STX_LAUNCH(k_norm_ln_split, dim3(gx, B), dim3(256), 0, st, d_lengths, info.partials, info.chunk_frames, info.chunks, T_pad,
-               padding_value, (const float*)raw, d_ln_weight, d_ln_bias, eps, a_planes, rows * 2 * kMel, d_features, d_mask);
+               padding_value, (const float*)raw, d_ln_weight, d_ln_bias, eps, a_planes, rows * 2 * kMel, d_features, d_mask,
+               info.cstat);
     return project_from_planes(a_planes, (int)rows, 2 * kMel, d_weight, d_bias, out_dim, b_planes, d_hidden, st);
 }
 

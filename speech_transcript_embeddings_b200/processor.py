@@ -12,11 +12,18 @@ The float32 cast, the peak-normalise (R/processor.py:91-92) and the trim to ``ma
 decoding are outside the hot path: they are delegated to the same third-party packages the reference uses and
 raise a clear error when those are not installed.
 
-Resampling (R/processor.py:82-86) runs on the device as well (``resample="device"``, the default): the polyphase
-resampler of ``librosa.resample(..., res_type="polyphase")`` (= ``scipy.signal.resample_poly``), with the per-clip
-peak reduced in the same pass.  The reference's own default ``res_type`` is ``"soxr_hq"``, whose arithmetic lives in
-the soxr C library and cannot be reproduced bit for bit; ``resample="librosa"`` keeps the reference's exact host call
-(needs librosa) for users who want that filter.
+Resampling (R/processor.py:82-86): the DEFAULT is the reference's own host call, ``librosa.resample(x, orig_sr=...,
+target_sr=16000)`` with its default ``res_type="soxr_hq"`` (``resample="librosa"``, needs librosa) -- that filter lives
+in the soxr C library and cannot be reproduced bit for bit, so a drop-in must not silently replace it.  Without librosa
+a non-16 kHz input raises and names the alternative.  ``resample="device"`` is the opt-in device path: the polyphase
+resampler of ``librosa.resample(..., res_type="polyphase")`` (= ``scipy.signal.resample_poly``) with the per-clip peak
+reduced in the same pass; it is a different low-pass than soxr_hq and changes the waveform (hence the features) at the
+1e-3 level.
+
+``padding_value`` (the value of the half-frame behind an odd-length clip and of cross-clip padding rows, mask 0 there):
+the reference reads it from the hub's ``preprocessor_config.json``.  ``None`` (default) looks for that file in the local
+HuggingFace cache; if it is not there (no network here), the w2v-bert-2.0 family gets 1.0 -- what its hub file is
+believed to hold (unverifiable offline) -- and everything else the class default 0.0.
 """
 from __future__ import annotations
 
@@ -31,6 +38,23 @@ from .feature_extraction import (B200SeamlessM4TFeatureExtractor, B200WhisperFea
                                  _layout)
 
 logger = logging.getLogger(__name__)
+
+
+def resolve_padding_value(audio_model_name: str) -> float:
+    """``padding_value`` of the extractor ``AutoFeatureExtractor.from_pretrained(audio_model_name)`` would build
+    (R/processor.py:36): the cached hub ``preprocessor_config.json`` if there is one, else the family default."""
+    try:
+        import json
+        from huggingface_hub import try_to_load_from_cache
+        path = try_to_load_from_cache(audio_model_name, "preprocessor_config.json")
+        if isinstance(path, str):
+            with open(path) as f:
+                cfg = json.load(f)
+            if "padding_value" in cfg:
+                return float(cfg["padding_value"])
+    except Exception:       # no hub package, unreadable cache: fall through to the family default
+        pass
+    return 1.0 if "w2v-bert" in audio_model_name.lower() else 0.0
 
 
 def make_feature_extractor(audio_model_name: str, device=None, **kwargs):
@@ -87,11 +111,14 @@ class AudioTextProcessor:
 
     def __init__(self, text_model_name="sentence-transformers/all-roberta-large-v1",
                  audio_model_name="facebook/w2v-bert-2.0", device=None, max_text_length=256,
-                 sampling_rate=16000, max_audio_length=480000, tokenizer=None, padding_value=0.0,
-                 resample="device"):
+                 sampling_rate=16000, max_audio_length=480000, tokenizer=None, padding_value=None,
+                 resample="librosa"):
         if resample not in ("device", "librosa"):
-            raise ValueError("resample must be 'device' (polyphase, on the GPU) or 'librosa' (the reference's host call)")
+            raise ValueError("resample must be 'librosa' (the reference's host call, the default) or 'device' "
+                             "(polyphase, on the GPU)")
         self.resample = resample
+        if padding_value is None:
+            padding_value = resolve_padding_value(audio_model_name)
         self.device = torch.device(device) if device is not None else torch.device(
             "cuda" if torch.cuda.is_available() else "cpu")
         self.max_text_length = max_text_length
@@ -134,8 +161,10 @@ class AudioTextProcessor:
             try:
                 import librosa
             except ImportError as e:
-                raise ImportError(f"resample='librosa': resampling {orig_sr} Hz -> {self.sampling_rate} Hz on the host "
-                                  "needs librosa, as in the reference (the default resample='device' does not)") from e
+                raise ImportError(f"resampling {orig_sr} Hz -> {self.sampling_rate} Hz the way the reference does "
+                                  "(librosa.resample, res_type='soxr_hq', R/processor.py:82-86) needs librosa; "
+                                  "AudioTextProcessor(resample='device') resamples on the GPU instead, with librosa's "
+                                  "'polyphase' filter (a different low-pass: not bit-compatible with the reference)") from e
             audio_array = librosa.resample(np.asarray(audio_array), orig_sr=orig_sr, target_sr=self.sampling_rate)
         # NB the reference takes the peak over the untrimmed clip (R/processor.py:91-97); so do we:
         # the trim happens on the device through the per-clip lengths

@@ -15,6 +15,21 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4
 
 
+def _oracle_errors(clips, feats):
+    """max-abs error of every clip's rows of `feats` ([B, T_pad/2, 160] host array) against the oracle run on that clip alone
+    (the oracle is NumPy: the clips are spread over a few threads, its FFTs release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        with np.errstate(all="ignore"):
+            ref = OK.extract([clips[i]])[0][0]
+        return float(np.abs(feats[i, :ref.shape[0]] - ref).max())
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        return np.array(list(ex.map(one, range(len(clips)))))
+
+
+
 @pytest.fixture(scope="module")
 def fe(cuda_device):
     return B200SeamlessM4TFeatureExtractor(device=cuda_device)
@@ -111,12 +126,12 @@ def test_cfg2_full_size_properties(fe):
     for i in (0, 31, 63):
         alone = fe(clips[i], sampling_rate=16000, return_tensors="pt")["input_features"]
         assert torch.equal(alone[0], x[i])                            # a clip does not depend on its batch
-    worst = 0.0
-    for i in (0, 17, 42, 63):
-        ref = OK.extract([clips[i]])[0][0]
-        worst = max(worst, float(np.abs(x[i].cpu().numpy() - ref).max()))
-    print(f"K cfg2 sample of 4 clips: max-abs {worst:.2e}")
-    assert worst <= TOL
+    # EVERY clip against the oracle: the case for float64 in the kernel is a tail event over the 1.9e5 frames of this batch
+    # (DESIGN.md section 4), which a sample of clips would not test
+    xh = x.cpu().numpy()
+    errs = _oracle_errors(clips, xh)
+    print(f"K cfg2, all 64 clips vs the oracle: max-abs {errs.max():.2e} (median clip {np.median(errs):.2e})")
+    assert errs.max() <= TOL
 
 
 def test_ill_conditioned_classes_are_reported_not_gated(fe):
@@ -221,17 +236,15 @@ def test_cfg3_variable_length_batch_512(fe):
         want_mask = (2 * np.arange(T_pad // 2)[None, :] + 1 < frames[:, None]).astype(np.int32)
         assert np.array_equal(m.cpu().numpy(), want_mask)
         raw = x.reshape(512, T_pad, 80)
-        worst = 0.0
+        valid = torch.arange(T_pad, device=raw.device)[None, :] < torch.from_numpy(frames).to(raw.device)[:, None]
+        assert not raw[~valid].any()                                          # padding_value = 0 rows past EVERY clip
         for i in (0, 101, 257, 388, 511, int(np.argmin(frames)), int(np.argmax(frames))):
-            assert not raw[i, frames[i]:].any()                               # padding_value = 0 rows past the clip
-            with np.errstate(all="ignore"):
-                ref = OK.extract([clips[i]])[0][0]
-            mine = x[i, :ref.shape[0]].cpu().numpy()
-            worst = max(worst, float(np.abs(mine - ref).max()))
             alone = fe(clips[i], sampling_rate=16000, return_tensors="pt")["input_features"][0]
             assert torch.equal(alone, x[i, :alone.shape[0]])                  # a clip does not depend on its batch
-        print(f"K cfg3 ({'whole seconds' if whole else 'arbitrary lengths'}) sample of 7 clips: max-abs {worst:.2e}")
-        assert worst <= TOL
+        errs = _oracle_errors(clips, x.cpu().numpy())                         # every one of the 512 clips
+        print(f"K cfg3 ({'whole seconds' if whole else 'arbitrary lengths'}), all 512 clips vs the oracle: "
+              f"max-abs {errs.max():.2e} (median clip {np.median(errs):.2e})")
+        assert errs.max() <= TOL
 
 
 def test_unaligned_clip_starts_take_the_plain_load_path(cuda_device):

@@ -153,3 +153,33 @@ def test_load_audio_pcm_widths(tmp_path, width):
         w.writeframes(raw)
     x, sr = load_audio(path)
     assert sr == 22050 and x.dtype == np.float32 and np.array_equal(x, want)
+
+
+def test_padding_value_resolution(tmp_path, monkeypatch):
+    """padding_value=None: cached hub preprocessor_config.json first, else 1.0 for the w2v-bert-2.0 family, 0.0 otherwise."""
+    import json
+    from speech_transcript_embeddings_b200 import processor
+    assert processor.resolve_padding_value("facebook/w2v-bert-2.0") in (0.0, 1.0)        # 1.0 unless a cache says otherwise
+    assert processor.resolve_padding_value("some/other-seamless-model") == 0.0
+    cfg = tmp_path / "preprocessor_config.json"
+    cfg.write_text(json.dumps({"padding_value": 0.5}))
+    import huggingface_hub
+    monkeypatch.setattr(huggingface_hub, "try_to_load_from_cache", lambda repo, name: str(cfg))
+    assert processor.resolve_padding_value("facebook/w2v-bert-2.0") == 0.5
+
+
+def test_default_resample_mode_is_the_reference_call_and_says_so_without_librosa():
+    """R/processor.py:82-86: the drop-in never substitutes another filter silently."""
+    import numpy as np
+    from speech_transcript_embeddings_b200.processor import AudioTextProcessor
+    proc = AudioTextProcessor(device="cpu")              # no CUDA probe on a CPU device; host-side preparation only
+    assert proc.resample == "librosa"
+    x = np.zeros(4800, np.float32)
+    assert proc._prepare(x, 16000).dtype == np.float32   # 16 kHz input needs no resampler
+    try:
+        import librosa  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="resample='device'"):
+            proc._prepare(x, 48000)
+    with pytest.raises(ValueError):
+        AudioTextProcessor(device="cpu", resample="nope")

@@ -27,7 +27,7 @@ def test_process_audio_array_recipe_k(cuda_device, kind):
     audio = synth.clip(kind, 52345, seed=8)
     out = proc.process_audio_array(audio, 16000)
     assert set(out) == {"input_features", "attention_mask_audio"}
-    ref_x, ref_m = OK.extract([_reference_prepare(audio, 40000)])
+    ref_x, ref_m = OK.extract([_reference_prepare(audio, 40000)], padding_value=proc.feature_extractor.padding_value)
     x, m = out["input_features"], out["attention_mask_audio"]
     assert x.device == cuda_device and x.dtype == torch.float32 and m.dtype == torch.int32
     assert tuple(x.shape) == ref_x.shape and np.array_equal(m.cpu().numpy(), ref_m)
@@ -69,10 +69,41 @@ def test_process_audio_file_wav_48k(cuda_device, tmp_path):
         w.writeframes(pcm.tobytes())
     audio, sr = load_audio(path)
     assert sr == 48000 and audio.dtype == np.float32
-    got = AudioTextProcessor(device=cuda_device).process_audio_file(str(path))
+    proc = AudioTextProcessor(device=cuda_device, resample="device")
+    got = proc.process_audio_file(str(path))
     xr = OR.resample_poly(audio, 48000, 16000)
     if np.abs(xr).max() > 1.0:
         xr = xr / np.abs(xr).max()
-    ref, mask = OK.extract([xr])
+    ref, mask = OK.extract([xr], padding_value=proc.feature_extractor.padding_value)
     assert np.abs(got["input_features"].cpu().numpy() - ref).max() <= 1e-4
     assert np.array_equal(got["attention_mask_audio"].cpu().numpy(), mask)
+
+
+def test_default_resampling_is_the_reference_host_call(cuda_device):
+    """R/processor.py:82-86: non-16 kHz audio goes through librosa.resample (soxr_hq) unless the device path is asked for."""
+    proc = AudioTextProcessor(device=cuda_device)
+    assert proc.resample == "librosa"
+    x = synth.clip("G", 48000, 4)
+    try:
+        import librosa
+    except ImportError:
+        with pytest.raises(ImportError, match="resample='device'"):
+            proc.process_audio_array(x, 48000)
+        return
+    got = proc.process_audio_array(x, 48000)
+    xr = librosa.resample(x, orig_sr=48000, target_sr=16000)
+    ref, mask = OK.extract([_reference_prepare(xr, 480000)], padding_value=proc.feature_extractor.padding_value)
+    assert np.abs(got["input_features"].cpu().numpy() - ref).max() <= 1e-4
+    assert np.array_equal(got["attention_mask_audio"].cpu().numpy(), mask)
+
+
+def test_padding_value_follows_the_hub_config_of_the_model_family(cuda_device):
+    """The half-frame behind an odd-length clip carries the extractor's padding_value (mask 0 there)."""
+    proc = AudioTextProcessor(device=cuda_device)                     # w2v-bert-2.0: 1.0 unless a cached hub config says otherwise
+    pv = proc.feature_extractor.padding_value
+    audio = synth.clip("G", 400 + 160 * 6, seed=2)                    # 7 frames: odd
+    out = proc.process_audio_array(audio, 16000)
+    x = out["input_features"].cpu().numpy()
+    assert x.shape == (1, 4, 160) and np.all(x[0, 3, 80:] == np.float32(pv))
+    assert out["attention_mask_audio"].cpu().numpy().tolist() == [[1, 1, 1, 0]]
+    assert AudioTextProcessor(device=cuda_device, padding_value=0.25).feature_extractor.padding_value == 0.25

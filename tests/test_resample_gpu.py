@@ -96,14 +96,14 @@ def test_full_size_properties(cuda_device, sr):
 
 def test_processor_resamples_on_the_device(cuda_device):
     """process_audio_array(x, 48000) == extractor(oracle-resampled x): R/processor.py:82-126 end to end."""
-    proc = AudioTextProcessor(device=cuda_device)
+    proc = AudioTextProcessor(device=cuda_device, resample="device")
     for sr, kind in ((48000, "G"), (44100, "loud")):
         x = synth.clip(kind, int(2.5 * sr) + 7, 3)
         got = proc.process_audio_array(x, sr)
         xr = OR.resample_poly(x, sr, 16000)
         if np.abs(xr).max() > 1.0:
             xr = xr / np.abs(xr).max()
-        ref, mask = OK.extract([xr[:480000]])
+        ref, mask = OK.extract([xr[:480000]], padding_value=proc.feature_extractor.padding_value)
         assert got["input_features"].shape == ref.shape
         assert np.abs(got["input_features"].cpu().numpy() - ref).max() <= 1e-4
         assert np.array_equal(got["attention_mask_audio"].cpu().numpy(), mask)
