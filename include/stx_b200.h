@@ -71,6 +71,23 @@ int         stx_profile_collect(char* h_names, float* h_ms, int cap);
  * Returns the number of doubles written (<= cap), or STX_EINVAL. */
 int64_t     stx_get_table(const char* name, double* h_out, int64_t cap);
 
+/* Host-side packing for the reference-signature call: the reference hands the extractor a list of ordinary (pageable)
+ * float32 arrays (R/processor.py:88-105, R/training/trainer_unfreeze.py:856-860); before the H2D copy can run at PCIe speed
+ * they have to be gathered into one pinned staging buffer.  Copies segment i (n_bytes[i] bytes at h_src[i]) to
+ * h_dst_base + dst_byte_offsets[i] with up to `threads` native threads of a persistent in-library pool (non-temporal stores,
+ * work split by bytes, not by segment).  Synchronous: the bytes are in place when it returns.  No CUDA call is made. */
+int         stx_host_pack(const void* const* h_src, const int64_t* n_bytes, void* h_dst_base, const int64_t* dst_byte_offsets,
+                          int count, int threads);
+/* The same copy as a pipelined job: segments [chunk_starts[c], chunk_starts[c + 1]) form chunk c (n_chunks + 1 entries); the
+ * chunks are packed in order on a native thread.  _begin returns a job handle (NULL on error) at once; _wait blocks until
+ * chunk `chunk` is in place (chunk < 0: all of them); _end joins the job and frees it (the sources and the destination must
+ * stay valid until then).  The caller overlaps the H2D copy of chunk c with the packing of chunk c + 1. */
+void*       stx_host_pack_begin(const void* const* h_src, const int64_t* n_bytes, void* h_dst_base,
+                                const int64_t* dst_byte_offsets, int count, const int32_t* chunk_starts, int n_chunks,
+                                int threads);
+int         stx_host_pack_wait(void* h_job, int chunk);
+int         stx_host_pack_end(void* h_job);
+
 /* ---------------------------------------------------------------------------------------------
  * Recipe K: Kaldi-style fbank + per-clip per-bin CMVN + pad + stride-2 stacking + mask.
  * Replaces SeamlessM4TFeatureExtractor.__call__ (TF/models/seamless_m4t/

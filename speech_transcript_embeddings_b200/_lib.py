@@ -21,6 +21,10 @@ _SIGNATURES = {
     "stx_profile_enable": (C.c_int, [C.c_int]),
     "stx_profile_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "stx_get_table": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64]),
+    "stx_host_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "stx_host_pack_begin": (C.c_void_p, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "stx_host_pack_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "stx_host_pack_end": (C.c_int, [C.c_void_p]),
     "stx_fbank_k_workspace": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "stx_fbank_k": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                               C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

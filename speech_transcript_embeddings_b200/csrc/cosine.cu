@@ -10,6 +10,7 @@
 //   c_pairwise    one warp per row: <a_i, b_i> * inv_a[i] * inv_b[i]
 //   c_split + c_nxm_tc   the N x M matrix on tcgen05 tensor cores with split-TF32 operands (see below)
 #include "stx_common.h"
+#include <cuda_bf16.h>
 #include <cuda.h>
 #include <algorithm>
 
@@ -139,11 +140,16 @@ c_pos_neg_loss(const float* __restrict__ per_sample, const float* __restrict__ s
 
 // ---- N x M contraction on the 5th-generation tensor cores (tcgen05, accumulators in TMEM) -------------------
 //
-// float32 accuracy from TF32 MMAs by operand splitting: x = hi + lo with hi = x truncated to TF32 (exactly
-// representable, so the tensor core's own fp32 -> tf32 conversion cannot change it) and lo = x - hi (exact);
-//   <a, b> ~= <a_hi, b_hi> + <a_lo, b_hi> + <a_hi, b_lo>          (the dropped <a_lo, b_lo> is ~2^-22 |a||b|)
-// run as ONE accumulation of 3 * D/32 k-blocks into the same TMEM tile.  Measured max-abs error vs float64 on
-// unit rows: ~2e-7 (single-pass TF32: 5e-5; the bar is 1e-5).
+// float32-grade accuracy from narrow MMAs by operand splitting: x = hi + lo,
+//   <a, b> ~= <a_hi, b_hi> + <a_lo, b_hi> + <a_hi, b_lo>
+// in one of two operand formats (TcGeom::bf16):
+//   TF32 (feature projection): hi = x truncated to TF32 (exactly representable, so the tensor core's own fp32 -> tf32
+//        conversion cannot change it), lo = x - hi (exact); the dropped <a_lo, b_lo> is ~2^-22 |a||b|.  K = 8 per MMA.
+//   BF16 (cosine scores, round 2): hi = bf16(x), lo = bf16(x - hi), both round-to-nearest: x - hi - lo <= 2^-18 |x|, so
+//        the dropped terms are <= 3 * 2^-18 sum|a_i b_i| in the worst case (1.1e-5 for unit rows whose products all have
+//        one sign) and ~1e-5 / sqrt(D) in practice: measured <= 2e-6 on unit rows incl. cos = 1 pairs (bar 1e-5).  K = 16
+//        per MMA at the same issue rate: half the tensor-pipe time of TF32, half the operand bytes (planes, L2 -> shared
+//        memory traffic, NVLink push of the gathered call).  cfg5: 0.125 -> see DESIGN.md.
 //
 //   c_split    one warp per row: scale by 1/||x|| (or 1), write hi and lo planes with rows zero-padded to a
 //              multiple of 32 floats (one 128-byte swizzle row per k-block)
@@ -162,6 +168,8 @@ constexpr unsigned kTmemCols = 512;             // two tiles in flight x two 128
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major A and B,
 // N >> 3 at [17,23), M >> 4 at [24,29)
 constexpr unsigned kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kTN >> 3) << 17) | ((unsigned)(kTM >> 4) << 24);
+// kind::f16 with BF16 operands (format 1 in both fields), F32 accumulator
+constexpr unsigned kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTN >> 3) << 17) | ((unsigned)(kTM >> 4) << 24);
 
 struct TcSmem {
     unsigned char a_hi[kStages][kTileBytes];    // [128 rows][128 B], 128-byte swizzle, 1024-byte aligned
@@ -205,6 +213,11 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdescBf16), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -229,7 +242,9 @@ struct SplitDst {
 };
 
 // hi / lo planes of both operands (rows [0, N) = a, [N, N + M) = b).  inv == nullptr: normalise unconditionally
-// with the norm computed here (no separate norm pass, no flags).
+// with the norm computed here (no separate norm pass, no flags).  kBf16: the planes are bfloat16 (rows of Dp elements, Dp a
+// multiple of 64; plane strides count bfloat16 elements), else float32 holding TF32 values (Dp a multiple of 32).
+template <bool kBf16>
 __global__ void __launch_bounds__(256)
 c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, int D, int Dp,
         const float* __restrict__ inv_a, const float* __restrict__ inv_b, const CosWs* __restrict__ ws, const SplitDst dst) {
@@ -244,6 +259,51 @@ c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, 
         else scale = (is_b ? ws->flag_b : ws->flag_a) ? (is_b ? inv_b : inv_a)[row] : 1.0f;
         const size_t off = (size_t)row * Dp;
         const bool vec_in = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+        if (kBf16) {
+            __nv_bfloat16* const a_pl = reinterpret_cast<__nv_bfloat16*>(dst.a_planes);
+            for (int i = 8 * lane; i < Dp; i += 256) {                 // Dp is a multiple of 64: whole groups of 8
+                float v[8];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (vec_in && i + 4 * h + 4 <= D) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(p + i + 4 * h));
+                        v[4 * h] = x.x * scale; v[4 * h + 1] = x.y * scale; v[4 * h + 2] = x.z * scale; v[4 * h + 3] = x.w * scale;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[4 * h + j] = i + 4 * h + j < D ? __ldg(p + i + 4 * h + j) * scale : 0.0f;
+                    }
+                }
+                unsigned hw[4], lw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+                    hw[j] = (unsigned)__bfloat16_as_ushort(h0) | ((unsigned)__bfloat16_as_ushort(h1) << 16);
+                    lw[j] = (unsigned)__bfloat16_as_ushort(l0) | ((unsigned)__bfloat16_as_ushort(l1) << 16);
+                }
+                const uint4 H = make_uint4(hw[0], hw[1], hw[2], hw[3]), L = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                if (!is_b) {
+                    *reinterpret_cast<uint4*>(a_pl + off + i) = H;
+                    *reinterpret_cast<uint4*>(a_pl + dst.a_plane_stride + off + i) = L;
+                } else if (dst.b_mc) {
+                    __nv_bfloat16* const mc = reinterpret_cast<__nv_bfloat16*>(dst.b_mc);
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 ::"l"(mc + off + i), "f"(__uint_as_float(H.x)), "f"(__uint_as_float(H.y)),
+                                   "f"(__uint_as_float(H.z)), "f"(__uint_as_float(H.w)) : "memory");
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 ::"l"(mc + dst.b_plane_stride + off + i), "f"(__uint_as_float(L.x)), "f"(__uint_as_float(L.y)),
+                                   "f"(__uint_as_float(L.z)), "f"(__uint_as_float(L.w)) : "memory");
+                } else {
+#pragma unroll 1
+                    for (int d = 0; d < dst.n_dst; ++d) {
+                        __nv_bfloat16* const bp = reinterpret_cast<__nv_bfloat16*>(dst.b_dst[d]);
+                        *reinterpret_cast<uint4*>(bp + off + i) = H;
+                        *reinterpret_cast<uint4*>(bp + dst.b_plane_stride + off + i) = L;
+                    }
+                }
+            }
+        } else
         for (int i = 4 * lane; i < Dp; i += 128) {                     // Dp is a multiple of 32: whole float4s
             float v[4];
             if (vec_in && i + 4 <= D) {
@@ -289,6 +349,21 @@ c_split(const float* __restrict__ a, const float* __restrict__ b, int N, int M, 
                 *dst.counter = 0;
             }
         }
+    }
+}
+
+// The two-set protocol of stx_cosine_nxm_gathered has no barrier between calls: it is safe only if, in EVERY call, every rank
+// acquires the flag of EVERY peer before its stream moves on (a peer's push of call e + 2 reuses the planes of call e).  The
+// GEMM's TMA producer acquires the flags of the slots it reads; a rank that has nothing to compute (no local rows, or no
+// columns at all), and the slots that hold no rows, are covered by this one-warp kernel instead.
+__global__ void c_acquire_flags(const unsigned* __restrict__ flags, int world, unsigned epoch) {
+    const int r = threadIdx.x;
+    if (r < world) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+            if ((int)(v - epoch) < 0) __nanosleep(64);
+        } while ((int)(v - epoch) < 0);
     }
 }
 
@@ -352,6 +427,7 @@ struct TcGeom {
     const unsigned* flags;          // flags[slot] reaches `epoch` when the slot's planes have landed (nullptr: local data)
     unsigned epoch;
     const float* bias;              // nullptr, or one value per output column added in the epilogue (feature projection)
+    int bf16;                       // operand planes are bfloat16 (64 elements per 128-byte k-block row), else TF32 in float32 (32)
     // retrieval mode (top-k): the epilogue does not write S; every (row, column tile) leaves its kTopK best scores and their
     // column indices (descending; ties: lower column first) in cand_val / cand_idx [row][column tile][kTopK]
     float* cand_val;
@@ -417,14 +493,15 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                     } while ((int)(v - g.epoch) < 0);
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
+                const int kelems = g.bf16 ? 2 * kTK : kTK;         // elements per 128-byte k-block row
                 for (int kb = 0; kb < kb_per_pass; ++kb, ++it) {
                     const int s = it % kStages, round = it / kStages;
                     if (round > 0) mbar_wait(&sm.empty[s], (unsigned)(round - 1) & 1u);
                     mbar_expect_tx(&sm.full[s], 4 * kTileBytes);
-                    tma_load_2d(sm.a_hi[s], &map_a, kb * kTK, ti.m0, &sm.full[s]);
-                    tma_load_2d(sm.a_lo[s], &map_a, kb * kTK, ti.m0 + g.a_plane_rows, &sm.full[s]);
-                    tma_load_2d(sm.b_hi[s], &map_b, kb * kTK, ti.b_row_hi, &sm.full[s]);
-                    tma_load_2d(sm.b_lo[s], &map_b, kb * kTK, ti.b_row_hi + g.b_plane_rows, &sm.full[s]);
+                    tma_load_2d(sm.a_hi[s], &map_a, kb * kelems, ti.m0, &sm.full[s]);
+                    tma_load_2d(sm.a_lo[s], &map_a, kb * kelems, ti.m0 + g.a_plane_rows, &sm.full[s]);
+                    tma_load_2d(sm.b_hi[s], &map_b, kb * kelems, ti.b_row_hi, &sm.full[s]);
+                    tma_load_2d(sm.b_lo[s], &map_b, kb * kelems, ti.b_row_hi + g.b_plane_rows, &sm.full[s]);
                 }
             }
         }
@@ -451,9 +528,15 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                     for (int k = 0; k < kTK / 8; ++k) {
                         const unsigned long long ah = umma_desc(sm.a_hi[s], k * 32), al = umma_desc(sm.a_lo[s], k * 32);
                         const unsigned long long bh = umma_desc(sm.b_hi[s], k * 32), bl = umma_desc(sm.b_lo[s], k * 32);
-                        umma_tf32(d, ah, bh, (kb | k) != 0);
-                        umma_tf32(dx, al, bh, (kb | k) != 0);
-                        umma_tf32(dx, ah, bl, 1);
+                        if (g.bf16) {               // 32 bytes per K step in both formats: 16 bfloat16 or 8 TF32
+                            umma_bf16(d, ah, bh, (kb | k) != 0);
+                            umma_bf16(dx, al, bh, (kb | k) != 0);
+                            umma_bf16(dx, ah, bl, 1);
+                        } else {
+                            umma_tf32(d, ah, bh, (kb | k) != 0);
+                            umma_tf32(dx, al, bh, (kb | k) != 0);
+                            umma_tf32(dx, ah, bl, 1);
+                        }
                     }
                     umma_commit(&sm.empty[s]);      // the stage is free once these MMAs have read it
                 }
@@ -607,7 +690,7 @@ c_topk_merge(const float* __restrict__ cand_val, const int* __restrict__ cand_id
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_map(CUtensorMap* map, const float* base, int rows, int Dp, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int rows, int Dp, int box_rows, bool bf16) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -617,10 +700,10 @@ int make_map(CUtensorMap* map, const float* base, int rows, int Dp, int box_rows
         fn = reinterpret_cast<EncodeTiledFn>(p);
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)Dp * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTK, (cuuint32_t)box_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Dp * (bf16 ? 2 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * kTK : kTK), (cuuint32_t)box_rows};        // 128 bytes per box row
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+    const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STX_EINVAL; }
@@ -628,13 +711,20 @@ int make_map(CUtensorMap* map, const float* base, int rows, int Dp, int box_rows
 }
 
 inline int padded_d(int D) { return (D + kTK - 1) / kTK * kTK; }
+inline int padded_d64(int D) { return (D + 2 * kTK - 1) / (2 * kTK) * (2 * kTK); }
+// operand format of the cosine contractions: bfloat16 hi / lo planes unless STX_COSINE_TF32=1 (A/B runs; every rank of a
+// gathered call must agree)
+inline bool cosine_bf16() {
+    static const bool v = [] { const char* e = std::getenv("STX_COSINE_TF32"); return !(e && e[0] == '1'); }();
+    return v;
+}
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-int launch_gemm(const float* a_planes, int a_rows_total, const float* b_planes, int b_rows_total, int Dp, const TcGeom& g,
+int launch_gemm(const void* a_planes, int a_rows_total, const void* b_planes, int b_rows_total, int Dp, const TcGeom& g,
                 int n_col_tiles, float* d_S, cudaStream_t st) {
     CUtensorMap ma, mb;
-    if (int rc = make_map(&ma, a_planes, a_rows_total, Dp, kTM)) return rc;
-    if (int rc = make_map(&mb, b_planes, b_rows_total, Dp, kTN)) return rc;
+    if (int rc = make_map(&ma, a_planes, a_rows_total, Dp, kTM, g.bf16 != 0)) return rc;
+    if (int rc = make_map(&mb, b_planes, b_rows_total, Dp, kTN, g.bf16 != 0)) return rc;
     static bool attr_set[64] = {false};
     int dev = 0;
     STX_CUDA(cudaGetDevice(&dev));
@@ -647,7 +737,7 @@ int launch_gemm(const float* a_planes, int a_rows_total, const float* b_planes, 
     if (dev >= 0 && dev < 64 && !sms[dev]) STX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = (long long)n_col_tiles * ((g.n_rows + kTM - 1) / kTM);
     const int ctas = (int)std::min<long long>(tiles, (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148);
-    STX_LAUNCH(c_nxm_tc, dim3(ctas), dim3(kTcThreads), smem_bytes, st, ma, mb, g, Dp / kTK, n_col_tiles, d_S);
+    STX_LAUNCH(c_nxm_tc, dim3(ctas), dim3(kTcThreads), smem_bytes, st, ma, mb, g, Dp / (g.bf16 ? 2 * kTK : kTK), n_col_tiles, d_S);
     return 0;
 }
 
@@ -724,17 +814,21 @@ int stx_cosine_nxm(const float* d_a, const float* d_b, int N, int M, int D, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CosWs* ws; float *inv_a, *inv_b;
     if (int rc = cosine_prepare(d_a, d_b, N, M, D, d_ws, ws_bytes, st, &ws, &inv_a, &inv_b, !always_normalize)) return rc;
-    const int Dp = padded_d(D);
+    // (the workspace is sized for float32 planes of padded_d(D) columns; bfloat16 planes of padded_d64(D) columns never need more)
+    const bool bf = cosine_bf16();
+    const int Dp = bf ? padded_d64(D) : padded_d(D);
     char* p = reinterpret_cast<char*>(inv_b) + align256(size_t(M) * sizeof(float));
-    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(size_t(N) * Dp * sizeof(float));
+    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(size_t(N) * padded_d(D) * sizeof(float));
     float* b_planes = reinterpret_cast<float*>(p);
     SplitDst dst = {};
     dst.a_planes = a_planes;  dst.a_plane_stride = size_t(N) * Dp;
     dst.b_dst[0] = b_planes;  dst.b_plane_stride = size_t(M) * Dp;  dst.n_dst = 1;
-    STX_LAUNCH(c_split, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
-               always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
+    if (bf) STX_LAUNCH(c_split<true>, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
+                       always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
+    else STX_LAUNCH(c_split<false>, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
+                    always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
     TcGeom g = {};
-    g.n_rows = N;  g.a_plane_rows = N;  g.b_plane_rows = M;  g.world = 1;
+    g.n_rows = N;  g.a_plane_rows = N;  g.b_plane_rows = M;  g.world = 1;  g.bf16 = bf;
     g.tiles_start[0] = 0;  g.tiles_start[1] = (M + kTN - 1) / kTN;
     g.slot[0] = 0;  g.m_count[0] = M;  g.col_start[0] = 0;  g.ldS = M;
     return launch_gemm(a_planes, 2 * N, b_planes, 2 * M, Dp, g, g.tiles_start[1], d_S, st);
@@ -765,9 +859,10 @@ int stx_cosine_topk(const float* d_a, const float* d_b, int N, int M, int D, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CosWs* ws; float *inv_a, *inv_b;
     if (int rc = cosine_prepare(d_a, d_b, N, M, D, d_ws, base, st, &ws, &inv_a, &inv_b, !always_normalize)) return rc;
-    const int Dp = padded_d(D);
+    const bool bf = cosine_bf16();
+    const int Dp = bf ? padded_d64(D) : padded_d(D);
     char* p = reinterpret_cast<char*>(inv_b) + align256(size_t(M) * sizeof(float));
-    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(size_t(N) * Dp * sizeof(float));
+    float* a_planes = reinterpret_cast<float*>(p);  p += 2 * align256(size_t(N) * padded_d(D) * sizeof(float));
     float* b_planes = reinterpret_cast<float*>(p);
     const int tiles = (M + kTN - 1) / kTN;
     char* c = static_cast<char*>(d_ws) + base;
@@ -776,10 +871,12 @@ int stx_cosine_topk(const float* d_a, const float* d_b, int N, int M, int D, int
     SplitDst dst = {};
     dst.a_planes = a_planes;  dst.a_plane_stride = size_t(N) * Dp;
     dst.b_dst[0] = b_planes;  dst.b_plane_stride = size_t(M) * Dp;  dst.n_dst = 1;
-    STX_LAUNCH(c_split, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
-               always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
+    if (bf) STX_LAUNCH(c_split<true>, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
+                       always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
+    else STX_LAUNCH(c_split<false>, dim3((N + M + 7) / 8), dim3(256), 0, st, d_a, d_b, N, M, D, Dp,
+                    always_normalize ? nullptr : inv_a, always_normalize ? nullptr : inv_b, ws, dst);
     TcGeom g = {};
-    g.n_rows = N;  g.a_plane_rows = N;  g.b_plane_rows = M;  g.world = 1;
+    g.n_rows = N;  g.a_plane_rows = N;  g.b_plane_rows = M;  g.world = 1;  g.bf16 = bf;
     g.tiles_start[0] = 0;  g.tiles_start[1] = tiles;
     g.slot[0] = 0;  g.m_count[0] = M;  g.col_start[0] = 0;  g.ldS = M;
     g.cand_val = cand_val;  g.cand_idx = cand_idx;
@@ -867,36 +964,50 @@ int stx_cosine_nxm_gathered(const float* d_a, const float* d_b, int n_local, int
         if (h_counts[r] < 0 || h_counts[r] > m_cap || !h_peer_symm[r]) { set_error("stx_cosine_nxm_gathered: bad shard %d", r); return STX_EINVAL; }
         M += h_counts[r];
     }
-    if (!d_a || !d_b || !d_S || !d_ws) { set_error("stx_cosine_nxm_gathered: null pointer"); return STX_EINVAL; }
+    if ((n_local > 0 && !d_a) || (h_counts[rank] > 0 && !d_b) || (n_local > 0 && M > 0 && !d_S) || !d_ws) {
+        set_error("stx_cosine_nxm_gathered: null pointer");           // (empty shards may come with null pointers)
+        return STX_EINVAL;
+    }
     size_t need = 0, symm = 0;
     stx_cosine_gather_sizes(n_local, m_cap, world, D, &need, &symm);
     if (ws_bytes < need) { set_error("stx_cosine_nxm_gathered: workspace %zu < %zu bytes", ws_bytes, need); return STX_ENOSPACE; }
     if (int rc = check_device()) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int Dp = padded_d(D);
-    const size_t planes = symm_planes_bytes(world, m_cap, Dp);
+    // the symmetric buffer is laid out for float32 planes of padded_d(D) columns (stx_cosine_gather_sizes); bfloat16 planes of
+    // padded_d64(D) columns use the front of every set
+    const bool bf = cosine_bf16();
+    const int Dp = bf ? padded_d64(D) : padded_d(D);
+    const size_t planes = symm_planes_bytes(world, m_cap, padded_d(D));
     const size_t set_bytes = planes + 256;                  // planes, then the flags of this set
     const size_t set_off = size_t(epoch & 1u) * set_bytes;  // calls alternate between two sets: see stx_b200.h
-    const size_t slot_floats = size_t(2) * m_cap * Dp;
+    const size_t slot_bytes = size_t(2) * m_cap * Dp * (bf ? 2 : 4);
     float* a_planes = static_cast<float*>(d_ws);
     SplitDst dst = {};
     dst.a_planes = a_planes;  dst.a_plane_stride = size_t(n_local) * Dp;
     dst.b_plane_stride = size_t(m_cap) * Dp;  dst.n_dst = world;
     for (int p = 0; p < world; ++p) {
         char* base = static_cast<char*>(h_peer_symm[p]) + set_off;
-        dst.b_dst[p] = reinterpret_cast<float*>(base) + size_t(rank) * slot_floats;       // my slot in peer p's buffer
+        dst.b_dst[p] = reinterpret_cast<float*>(base + size_t(rank) * slot_bytes);        // my slot in peer p's buffer
         dst.flags[p] = reinterpret_cast<unsigned*>(base + planes);
     }
-    if (d_multicast) dst.b_mc = reinterpret_cast<float*>(static_cast<char*>(d_multicast) + set_off) + size_t(rank) * slot_floats;
+    if (d_multicast) dst.b_mc = reinterpret_cast<float*>(static_cast<char*>(d_multicast) + set_off + size_t(rank) * slot_bytes);
     char* mine = static_cast<char*>(h_peer_symm[rank]) + set_off;
     dst.flag_index = rank;  dst.epoch = epoch;
     dst.counter = reinterpret_cast<unsigned*>(static_cast<char*>(h_peer_symm[rank]) + 2 * set_bytes);
     // normalise + split + all-gather over NVLink (P2P stores into every peer's slot) in one kernel
-    STX_LAUNCH(c_split, dim3((n_local + h_counts[rank] + 7) / 8), dim3(256), 0, st, d_a, d_b, n_local, h_counts[rank], D, Dp,
-               nullptr, nullptr, nullptr, dst);
+    // (an empty shard still launches one CTA: it has nothing to store but it publishes this rank's flag)
+    if (bf) STX_LAUNCH(c_split<true>, dim3(std::max(1, (n_local + h_counts[rank] + 7) / 8)), dim3(256), 0, st, d_a, d_b, n_local,
+                       h_counts[rank], D, Dp, nullptr, nullptr, nullptr, dst);
+    else STX_LAUNCH(c_split<false>, dim3(std::max(1, (n_local + h_counts[rank] + 7) / 8)), dim3(256), 0, st, d_a, d_b, n_local,
+                    h_counts[rank], D, Dp, nullptr, nullptr, nullptr, dst);
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(mine + planes);
+    bool empty_slot = false;
+    for (int r = 0; r < world; ++r) empty_slot |= h_counts[r] == 0;
+    if (n_local == 0 || M == 0 || empty_slot)       // flags the GEMM below will not acquire (see c_acquire_flags)
+        STX_LAUNCH(c_acquire_flags, dim3(1), dim3(32), 0, st, my_flags, world, epoch);
     if (n_local == 0 || M == 0) return 0;
     TcGeom g = {};
-    g.n_rows = n_local;  g.a_plane_rows = n_local;  g.b_plane_rows = m_cap;  g.world = world;  g.ldS = M;
+    g.n_rows = n_local;  g.a_plane_rows = n_local;  g.b_plane_rows = m_cap;  g.world = world;  g.ldS = M;  g.bf16 = bf;
     int col = 0;
     for (int r = 0; r < world; ++r) { g.m_count[r] = h_counts[r]; g.col_start[r] = col; col += h_counts[r]; }
     int tiles = 0;

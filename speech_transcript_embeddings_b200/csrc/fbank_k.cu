@@ -122,19 +122,40 @@ struct KTables {
     int   melfirst[kMel];        // first FFT bin of the padded filter of mel bin m
 };
 
+// Precision study (north_star: "the choice evidenced by ncu"; profiles/r02_k_precision.md).  The single-group kernel k_frames
+// (STX_K_SINGLE=1) can be built with its first pass (pre-emphasis, window, real DFT-32, twiddles) and / or its second pass
+// (exchange, DFT-16, DC correction, power) in float32: tools/ab_build.py f32=-DSTX_K_P1_F32=1,-DSTX_K_P2_F32=1 etc.
+// The shipped kernels are float64 in both (see the header comment for why).
+#ifndef STX_K_P1_F32
+#define STX_K_P1_F32 0
+#endif
+#ifndef STX_K_P2_F32
+#define STX_K_P2_F32 0
+#endif
+template <bool F32> struct real_of { using type = double; using pair = double2; };
+template <> struct real_of<true> { using type = float; using pair = float2; };
+using r1_t = real_of<STX_K_P1_F32 != 0>::type;    // pass-1 arithmetic
+using r2_t = real_of<STX_K_P2_F32 != 0>::type;    // exchange and pass-2 arithmetic
+using r2x2_t = real_of<STX_K_P2_F32 != 0>::pair;
+#if STX_K_P1_F32 || STX_K_P2_F32
+__constant__ float  c_win_f[16][25];
+__constant__ float2 c_tw_f[16][16];
+__constant__ float2 c_wh_f[16][16];
+#endif
+
 struct Smem {
-    double2 ex[15][16][kTile];   // pass-1 output rows k1 = 1..15: [k1 - 1][n2][lane]; later aliased by the staged
+    r2x2_t  ex[15][16][kTile];   // pass-1 output rows k1 = 1..15: [k1 - 1][n2][lane]; later aliased by the staged
                                  // log-mel rows and the statistics reduction
-    double  ex0[16][kTile];      // row k1 = 0  (real)
-    double  ex16[16][kTile];     // row k1 = 16 (real)
+    r2_t    ex0[16][kTile];      // row k1 = 0  (real)
+    r2_t    ex16[16][kTile];     // row k1 = 16 (real)
     union {
-        double d[kDBuf];         // pre-emphasised samples of the tile (float64), rows of 161
-        float  P[256][kTile];    // power spectrum [bin][lane] (pass 2 onwards); row 0 is zeroed every tile
+        r1_t  d[kDBuf];          // pre-emphasised samples of the tile (float64), rows of 161
+        float P[256][kTile];     // power spectrum [bin][lane] (pass 2 onwards); row 0 is zeroed every tile
     } u;
     float   stage[kStage];       // raw PCM of the next tile, landed by cp.async.bulk
-    double  psum[kTile][17];     // per-warp sums of d, [lane][n2]
-    double  cval[kTile];         // 0.03 * mean of each frame
-    double  xb[kTile];           // 0.97 (x[399] - x[-1]) of each frame
+    r1_t    psum[kTile][17];     // per-warp sums of d, [lane][n2]
+    r2_t    cval[kTile];         // 0.03 * mean of each frame
+    r1_t    xb[kTile];           // 0.97 (x[399] - x[-1]) of each frame
     float   melw[kMelWeights];
     int     melfirst[kMel];
     unsigned long long mbar;     // completion barrier of the bulk copy
@@ -142,7 +163,8 @@ struct Smem {
 };
 static_assert(sizeof(Smem) <= 227 * 1024, "one CTA per SM must fit in 227 KB");
 static_assert(offsetof(Smem, stage) % 16 == 0, "bulk-copy destination alignment");
-static_assert(kTile * kOutRow * sizeof(float) <= sizeof(double2) * 15 * 16 * kTile, "staged rows alias the exchange area");
+static_assert(kTile * kOutRow * sizeof(float) <= sizeof(r2x2_t) * 15 * 16 * kTile, "staged rows alias the exchange area");
+static_assert(3 * kStatThreads * sizeof(unsigned long long) <= sizeof(r2x2_t) * 15 * 16 * kTile, "statistics reduction aliases the exchange area");
 
 // ln(x) for normal positive x (the mel floor guarantees it): exponent + MUFU.LG2 of the mantissa.
 // |error| <= ~0.6 ulp of the result for results of magnitude 10..30 (the mantissa's log2 is in [0, 1), where
@@ -165,6 +187,7 @@ __device__ __forceinline__ float ln_pos(float x) {
 // bits into place.  Truncation instead of round-to-nearest (<= 1 float32 ulp, 1.2e-7 relative on a value whose LOGARITHM
 // is compared at 1e-4); anything below 2^-126 (exact zeros: digital silence) becomes a denormal <= 7 * 2^-149, i.e. zero for
 // the mel floor that follows.
+__device__ __forceinline__ float power_to_f32(float p) { return p; }
 __device__ __forceinline__ float power_to_f32(double p) {
     const unsigned hi = (unsigned)__double2hiint(p), lo = (unsigned)__double2loint(p);
     const unsigned h = max(hi, 0x38000000u) - 0x38000000u;
@@ -186,6 +209,25 @@ __device__ __forceinline__ double2 lds_v2f64(const double2* p) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_u32(p)));
     return v;
 }
+__device__ __forceinline__ float lds_f64(const float* p) {          // (float32 builds of the precision study)
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ float2 lds_v2f64(const float2* p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(smem_u32(p)));
+    return v;
+}
+// warp-uniform tables in the precision of the pass that reads them
+__device__ __forceinline__ double  tab_win(int r, int n, double) { return c_win[r][n]; }
+__device__ __forceinline__ double2 tab_tw(int r, int k, double) { return c_tw[r][k]; }
+__device__ __forceinline__ double2 tab_wh(int r, int k, double) { return c_wh[r][k]; }
+#if STX_K_P1_F32 || STX_K_P2_F32
+__device__ __forceinline__ float  tab_win(int r, int n, float) { return c_win_f[r][n]; }
+__device__ __forceinline__ float2 tab_tw(int r, int k, float) { return c_tw_f[r][k]; }
+__device__ __forceinline__ float2 tab_wh(int r, int k, float) { return c_wh_f[r][k]; }
+#endif
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -328,27 +370,27 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             if (tid < 3 * kHop) {
                 const int r0 = tid / kHop, c0 = tid - r0 * kHop;
                 const float* src = sm.stage + kLead + r0 * kHop + c0;
-                double* dst = sm.u.d + r0 * kDRow + c0;
+                r1_t* dst = sm.u.d + r0 * kDRow + c0;
 #pragma unroll
                 for (int j = 0; j < 12; ++j) {
                     if (j < 11 || r0 * kHop + c0 < kTileSamples - 33 * kHop) {      // rows 0..32 are whole, row 33 holds 80 samples
                         float xm = src[3 * kHop * j - 1], xi = src[3 * kHop * j];
                         if (kPeak) { xm = xm / peak; xi = xi / peak; }
-                        dst[3 * kDRow * j] = fma(-0.97, (double)xm, (double)xi);
+                        dst[3 * kDRow * j] = codelets::fma_((r1_t)-0.97, (r1_t)xm, (r1_t)xi);
                     }
                 }
             }
             if (tid < kTile) {
                 float xa = sm.stage[kLead + tid * kHop + kFrame - 1], xz = sm.stage[kLead - 1 + tid * kHop];
                 if (kPeak) { xa = xa / peak; xz = xz / peak; }
-                sm.xb[tid] = 0.97 * ((double)xa - (double)xz);
+                sm.xb[tid] = (r1_t)0.97 * ((r1_t)xa - (r1_t)xz);
             }
         } else {
 #pragma unroll 1
             for (int i = tid; i < kTileSamples; i += kThreads)
-                sm.u.d[i + (unsigned)i / kHop] = fma(-0.97, (double)sample(s0 + i - 1), (double)sample(s0 + i));
+                sm.u.d[i + (unsigned)i / kHop] = codelets::fma_((r1_t)-0.97, (r1_t)sample(s0 + i - 1), (r1_t)sample(s0 + i));
             if (tid < kTile)
-                sm.xb[tid] = 0.97 * ((double)sample(s0 + tid * kHop + kFrame - 1) - (double)sample(s0 + tid * kHop - 1));
+                sm.xb[tid] = (r1_t)0.97 * ((r1_t)sample(s0 + tid * kHop + kFrame - 1) - (r1_t)sample(s0 + tid * kHop - 1));
         }
     };
     auto prefetch = [&](const int tn) {             // PCM of the tile at frame tn lands while the tile before it is transformed
@@ -366,12 +408,12 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
       if (t0 >= t_begin) {
         // ---- window + pass 1 (warp = n2) ----
         {
-            const double* D = sm.u.d + kDRow * lane + warp;
-            double y[25];
-            double sa = 0.0, sb = 0.0;
+            const r1_t* D = sm.u.d + kDRow * lane + warp;
+            r1_t y[25];
+            r1_t sa = 0, sb = 0;
             // first-use order of the radix-4 decimation in time: y[q], y[q+16], y[q+8], y[q+24], y[q+4], y[q+20], y[q+12]
             constexpr int kOrder1[25] = {0, 16, 8, 24, 4, 20, 12, 1, 17, 9, 5, 21, 13, 2, 18, 10, 6, 22, 14, 3, 19, 11, 7, 23, 15};
-            double v1[25];
+            r1_t v1[25];
 #pragma unroll
             for (int j = 0; j < 25; ++j) {
                 const int n1 = kOrder1[j];
@@ -379,18 +421,21 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             }
 #pragma unroll
             for (int n1 = 0; n1 < 25; ++n1) {
-                y[n1] = c_win[warp][n1] * v1[n1];
+                y[n1] = tab_win(warp, n1, r1_t()) * v1[n1];
                 if (n1 & 1) sb += v1[n1]; else sa += v1[n1];
             }
             sm.psum[lane][warp] = sa + sb;
-            double re[17], im[17];
-            codelets::k_pass1<double>(y, re, im);
-            sm.ex0[warp][lane] = re[0];
-            sm.ex16[warp][lane] = re[16];
+            r1_t re[17], im[17];
+            codelets::k_pass1<r1_t>(y, re, im);
+            sm.ex0[warp][lane] = (r2_t)re[0];
+            sm.ex16[warp][lane] = (r2_t)re[16];
 #pragma unroll
             for (int k1 = 1; k1 < 16; ++k1) {
-                const double2 t = *reinterpret_cast<const double2*>(&c_tw[warp][k1]);
-                sm.ex[k1 - 1][warp][lane] = make_double2(fma(re[k1], t.x, -(im[k1] * t.y)), fma(re[k1], t.y, im[k1] * t.x));
+                const auto t = tab_tw(warp, k1, r1_t());
+                r2x2_t o;
+                o.x = (r2_t)codelets::fma_(re[k1], t.x, -(im[k1] * t.y));
+                o.y = (r2_t)codelets::fma_(re[k1], t.y, im[k1] * t.x);
+                sm.ex[k1 - 1][warp][lane] = o;
             }
         }
         __syncthreads();                            // exchange complete; d is dead, its storage becomes the power spectrum
@@ -398,12 +443,12 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         // ---- c = 0.03 * mean(frame): warp w sums the 16 partials of frames 2 w and 2 w + 1 ----
         {
             const int fr = 2 * warp + (lane >> 4), r = lane & 15;
-            double v = sm.psum[fr][r];
+            r1_t v = sm.psum[fr][r];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
-            if (r == 0) sm.cval[fr] = (v - sm.xb[fr]) * (1.0 / 400.0);
+            if (r == 0) sm.cval[fr] = (r2_t)((v - sm.xb[fr]) * (r1_t)(1.0 / 400.0));
             if (warp == 1) sm.u.P[0][lane] = 0.0f;   // padded mel filters may touch bin 0 with a zero weight
             // c is only needed after the DFT-16 below: one arrival per warp on an mbarrier now, the wait is there,
             // so that no warp idles here
@@ -413,38 +458,38 @@ k_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
 
         // ---- pass 2 (warp = k1), DC correction, power ----
         {
-            double c = 0.0;
-            auto put = [&](int bin, double xr, double xi, double2 wh) {
-                const double a = fma(-c, wh.x, xr), bb = fma(-c, wh.y, xi);
-                sm.u.P[bin][lane] = power_to_f32(fma(a, a, bb * bb));
+            r2_t c = 0;
+            auto put = [&](int bin, r2_t xr, r2_t xi, r2x2_t wh) {
+                const r2_t a = codelets::fma_(-c, wh.x, xr), bb = codelets::fma_(-c, wh.y, xi);
+                sm.u.P[bin][lane] = power_to_f32(codelets::fma_(a, a, bb * bb));
             };
             if (warp == 0) {
-                double a[16], r[16];
+                r2_t a[16], r[16];
 #pragma unroll
                 for (int n2 = 0; n2 < 16; ++n2) { a[n2] = sm.ex0[n2][lane]; r[n2] = sm.ex16[n2][lane]; }
-                double e0r[7], e0i[7], e16r[8], e16i[8];
-                codelets::k_pass2_edge<double>(a, r, e0r, e0i, e16r, e16i);
+                r2_t e0r[7], e0i[7], e16r[8], e16i[8];
+                codelets::k_pass2_edge<r2_t>(a, r, e0r, e0i, e16r, e16i);
                 mbar_wait(&sm.cbar, cparity);
                 c = sm.cval[lane];
 #pragma unroll
-                for (int k2 = 1; k2 < 8; ++k2) put(32 * k2, e0r[k2 - 1], e0i[k2 - 1], c_wh[0][k2]);
+                for (int k2 = 1; k2 < 8; ++k2) put(32 * k2, e0r[k2 - 1], e0i[k2 - 1], tab_wh(0, k2, r2_t()));
 #pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) put(16 + 32 * k2, e16r[k2], e16i[k2], c_wh[0][8 + k2]);
+                for (int k2 = 0; k2 < 8; ++k2) put(16 + 32 * k2, e16r[k2], e16i[k2], tab_wh(0, 8 + k2, r2_t()));
             } else {
-                double xr[16], xi[16], yr[16], yi[16];
+                r2_t xr[16], xi[16], yr[16], yi[16];
                 constexpr int kOrder2[16] = {0, 8, 4, 12, 1, 9, 5, 13, 2, 10, 6, 14, 3, 11, 7, 15};
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n2 = kOrder2[j];
-                    const double2 v = lds_v2f64(&sm.ex[warp - 1][n2][lane]);
+                    const r2x2_t v = lds_v2f64(&sm.ex[warp - 1][n2][lane]);
                     xr[n2] = v.x; xi[n2] = v.y;
                 }
-                codelets::dft16<double>(xr, xi, yr, yi);
+                codelets::dft16<r2_t>(xr, xi, yr, yi);
                 mbar_wait(&sm.cbar, cparity);
                 c = sm.cval[lane];
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2)
-                    put(k2 < 8 ? warp + 32 * k2 : 512 - warp - 32 * k2, yr[k2], yi[k2], c_wh[warp][k2]);
+                    put(k2 < 8 ? warp + 32 * k2 : 512 - warp - 32 * k2, yr[k2], yi[k2], tab_wh(warp, k2, r2_t()));
             }
             cparity ^= 1;
         }
@@ -1269,6 +1314,22 @@ int get_tables(const KTables** out) {
         for (int k1 = 0; k1 < 16; ++k1)
             for (int k2 = 0; k2 < 16; ++k2) wh[k1][k2] = what(k1 + 32 * k2);
         for (int k2 = 0; k2 < 8; ++k2) wh[0][8 + k2] = what(16 + 32 * k2);     // row 0: bins 32 k2 and 16 + 32 k2
+#if STX_K_P1_F32 || STX_K_P2_F32
+        {
+            static float win_f[16][25];
+            static float2 tw_f[16][16], wh_f[16][16];
+            for (int i = 0; i < 16; ++i) {
+                for (int j = 0; j < 25; ++j) win_f[i][j] = (float)win[i][j];
+                for (int j = 0; j < 16; ++j) {
+                    tw_f[i][j] = make_float2((float)tw[i][j].x, (float)tw[i][j].y);
+                    wh_f[i][j] = make_float2((float)wh[i][j].x, (float)wh[i][j].y);
+                }
+            }
+            STX_CUDA(cudaMemcpyToSymbol(c_win_f, win_f, sizeof(win_f)));
+            STX_CUDA(cudaMemcpyToSymbol(c_tw_f, tw_f, sizeof(tw_f)));
+            STX_CUDA(cudaMemcpyToSymbol(c_wh_f, wh_f, sizeof(wh_f)));
+        }
+#endif
         STX_CUDA(cudaMemcpyToSymbol(c_win, win, sizeof(win)));
         STX_CUDA(cudaMemcpyToSymbol(c_tw, tw, sizeof(tw)));
         STX_CUDA(cudaMemcpyToSymbol(c_wh, wh, sizeof(wh)));

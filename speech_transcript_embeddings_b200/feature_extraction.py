@@ -19,17 +19,18 @@ the call costs about max(H2D, D2H) over PCIe instead of their sum.
 """
 from __future__ import annotations
 
+import ctypes as C
 import logging
 import os
 import threading
+import weakref
 from collections import UserDict
-from concurrent.futures import ThreadPoolExecutor
 from typing import Sequence
 
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 logger = logging.getLogger(__name__)
 
@@ -52,39 +53,54 @@ class BatchFeature(UserDict):
         return self
 
 
-_pool = None
-_pool_lock = threading.Lock()
-
-
-def _copy_pool() -> ThreadPoolExecutor:
-    """Worker threads for host-side packing (NumPy's memcpy releases the GIL)."""
-    global _pool
-    with _pool_lock:
-        if _pool is None:
-            _pool = ThreadPoolExecutor(max_workers=max(1, min(8, (os.cpu_count() or 2) - 1)),
-                                       thread_name_prefix="stx-pack")
-        return _pool
+def pack_threads() -> int:
+    """Native threads one packing job may use: the cores this process may run on, shared between the ranks of the node
+    (torchrun exports LOCAL_WORLD_SIZE), at most 16 -- beyond that the copy is bound by host memory bandwidth."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    return max(1, min(16, cores // ranks))
 
 
 class PackedClips:
     """Clips packed back to back (128-byte aligned) in one float32 buffer, plus per-clip offsets/lengths.
 
-    ``bounds`` / ``ready`` (optional): clip ranges whose packing is still running on worker threads, one future per
-    clip, grouped per range; consumers wait for a range right before they copy it to the device."""
+    ``bounds`` (optional): the clip ranges of the pipeline chunks.  ``job`` (optional): the native packing job
+    (``stx_host_pack_begin``) that is still filling the buffer chunk by chunk; consumers call ``wait(i)`` right before they
+    copy chunk ``i`` to the device.  ``stage``: the pinned staging buffer of the extractor's pool this object owns (it goes
+    back to the pool when the object dies and the copies out of it have drained)."""
 
-    def __init__(self, pcm: torch.Tensor, offsets: np.ndarray, lengths: np.ndarray, bounds=None, ready=None):
+    def __init__(self, pcm: torch.Tensor, offsets: np.ndarray, lengths: np.ndarray, bounds=None, job=None, stage=None,
+                 keep=None):
         self.pcm = pcm                      # pinned host tensor or CUDA tensor, float32 [total]
         self.offsets = offsets              # int64 [B] (host)
         self.lengths = lengths              # int32 [B] (host)
         self.bounds = bounds
-        self.ready = ready
+        self.stage = stage
+        self._job = job                     # native handle, or None once the job has been joined
+        self._keep = keep                   # the source arrays and the job's argument arrays stay alive while it runs
 
     def wait(self, i: int | None = None):
-        if self.ready is None:
+        if self._job is None:
             return
-        for group in (self.ready if i is None else [self.ready[i]]):
-            for f in group:
-                f.result()
+        lib = _lib.load()
+        _lib.check(lib.stx_host_pack_wait(self._job, -1 if i is None else int(i)), "stx_host_pack_wait")
+        if i is None or (self.bounds is not None and i >= len(self.bounds) - 1):
+            self._finish()
+
+    def _finish(self):
+        if self._job is not None:
+            job, self._job = self._job, None
+            _lib.load().stx_host_pack_end(job)
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self._finish()                  # joins the job: nothing writes into the staging buffer after this object is gone
+        except Exception:
+            pass
 
     @property
     def batch_size(self) -> int:
@@ -104,22 +120,43 @@ def _layout(lengths: np.ndarray):
     return offsets, total
 
 
-class _HostStage:
-    """Grow-only pinned staging buffers, reused across calls (guarded by an event)."""
+class _Stage:
+    """One pinned staging buffer of the pool."""
+
+    def __init__(self, n_float: int):
+        self.pcm = torch.empty(max(n_float, 1), dtype=torch.float32, pin_memory=True)
+        self.owner = None                   # weakref to the PackedClips that holds it (its death joins the packing job)
+        self.event = None                   # CUDA event after the last copy out of the buffer that was enqueued
+
+    def free(self) -> bool:
+        if self.owner is not None and self.owner() is not None:
+            return False
+        return self.event is None or self.event.query()
+
+
+class _StagePool:
+    """Pinned staging buffers of one extractor.  A buffer is reused only when the PackedClips that held it is gone (which
+    joins its packing job) and the H2D copies enqueued from it have completed; otherwise another buffer is allocated, so a
+    caller may hold several PackedClips (or pack batch i + 1 while batch i is in flight) safely."""
 
     def __init__(self):
-        self.pcm = None
-        self.meta = None
-        self.event = None
+        self.stages = []
+        self.lock = threading.Lock()
 
-    def get(self, n_float: int, n_meta: int):
-        if self.event is not None:
-            self.event.synchronize()        # the previous call's H2D copies have drained
-        if self.pcm is None or self.pcm.numel() < n_float:
-            self.pcm = torch.empty(max(n_float, 1), dtype=torch.float32, pin_memory=True)
-        if self.meta is None or self.meta.numel() < n_meta:
-            self.meta = torch.empty(max(n_meta, 1), dtype=torch.int64, pin_memory=True)
-        return self.pcm, self.meta
+    def acquire(self, n_float: int) -> _Stage:
+        with self.lock:
+            best = None
+            for st in self.stages:
+                if st.free() and st.pcm.numel() >= n_float and (best is None or st.pcm.numel() < best.pcm.numel()):
+                    best = st
+            if best is None:
+                # drop free buffers that are too small (grow-only in effect), then allocate
+                self.stages = [st for st in self.stages if not (st.free() and st.pcm.numel() < n_float)]
+                best = _Stage(n_float)
+                self.stages.append(best)
+            best.event = None
+            best.owner = None
+            return best
 
 
 def _as_clip_list(raw_speech, max_dims: int, cls_name: str):
@@ -152,7 +189,7 @@ class _B200ExtractorBase:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         self.device = torch.device(device) if device is not None else None
-        self._stage = _HostStage()
+        self._stages = _StagePool()
 
     def _check_rate(self, sampling_rate):
         if sampling_rate is not None:
@@ -231,6 +268,8 @@ class _B200ExtractorBase:
                 pcm_d[lo:hi].copy_(packed.pcm[lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
+            if packed.stage is not None:
+                packed.stage.event = ev_in                       # the staging buffer is busy until this copy has drained
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in)
                 launch(pcm_d[lo:hi], off_d[b0:b1], len_d[b0:b1], b0, b1, int(packed.lengths[b0:b1].max()))
@@ -244,29 +283,46 @@ class _B200ExtractorBase:
         cur.wait_stream(s_run)                                   # device buffers may be reused by the caller's stream
 
     # -- host -> device ----------------------------------------------------------------------
-    PACK_THREADS_MIN_BYTES = 4 << 20     # below this a plain loop is faster than handing work to the pool
+    FIRST_CHUNK_BYTES = 3 << 20          # a small first chunk: the H2D pipeline starts after ~50 us of packing
 
     def pack(self, clips: Sequence[np.ndarray]) -> PackedClips:
-        """Copy clips into one pinned host buffer (reused across calls).  Large batches are copied by worker
-        threads, one task per clip, and the returned object carries the futures grouped per pipeline chunk: the chunked pipeline
-        starts the H2D copy of chunk 0 while later chunks are still being packed."""
+        """Gather the clips (ordinary pageable arrays) into one pinned host buffer of the extractor's pool.
+
+        The copy runs in the library (``stx_host_pack_begin``: a native job, non-temporal stores, all the cores this rank
+        may use), one pipeline chunk after the other; the returned object waits per chunk, so the chunked pipeline starts
+        the H2D copy of chunk 0 while later chunks are still being packed."""
         lengths = np.fromiter((c.size for c in clips), dtype=np.int32, count=len(clips))
         offsets, total = _layout(lengths)
-        pcm, _ = self._stage.get(total, 2 * len(clips))
-        view = pcm.numpy()
-
-        def copy_range(b0, b1):
-            for i in range(b0, b1):
-                o = int(offsets[i])
-                view[o:o + clips[i].size] = clips[i]
-
-        if total * 4 < self.PACK_THREADS_MIN_BYTES or len(clips) < 2:
-            copy_range(0, len(clips))
-            return PackedClips(pcm[:total], offsets, lengths)
+        stage = self._stages.acquire(total)
+        pcm = stage.pcm[:total]
+        lib = _lib.load()
+        if not len(clips):
+            packed = PackedClips(pcm, offsets, lengths, [], None, stage)
+            stage.owner = weakref.ref(packed)
+            return packed
         bounds = self.chunk_bounds(offsets, lengths)
-        pool = _copy_pool()
-        ready = [[pool.submit(copy_range, i, i + 1) for i in range(b0, b1)] for b0, b1 in bounds]   # in clip order
-        return PackedClips(pcm[:total], offsets, lengths, bounds, ready)
+        if len(bounds) > 1 and self.FIRST_CHUNK_BYTES < self.CHUNK_BYTES:
+            first = self.chunk_bounds(offsets[:bounds[0][1]], lengths[:bounds[0][1]], self.FIRST_CHUNK_BYTES)
+            bounds = first + bounds[1:]
+        src = np.fromiter((c.ctypes.data for c in clips), dtype=np.uint64, count=len(clips))
+        nbytes = lengths.astype(np.int64) * 4
+        dst_off = offsets * 4
+        starts = np.array([b0 for b0, _ in bounds] + [len(clips)], dtype=np.int32)
+        if total * 4 < self.PACK_INLINE_BYTES:
+            _lib.check(lib.stx_host_pack(src.ctypes.data, nbytes.ctypes.data, pcm.data_ptr(), dst_off.ctypes.data, len(clips), 1),
+                       "stx_host_pack")
+            job, keep = None, None
+        else:
+            job = lib.stx_host_pack_begin(src.ctypes.data, nbytes.ctypes.data, pcm.data_ptr(), dst_off.ctypes.data, len(clips),
+                                          starts.ctypes.data, len(bounds), pack_threads())
+            if not job:
+                _lib.check(-1, "stx_host_pack_begin")
+            keep = (clips, src, nbytes, dst_off, starts)
+        packed = PackedClips(pcm, offsets, lengths, bounds, job, stage, keep)
+        stage.owner = weakref.ref(packed)
+        return packed
+
+    PACK_INLINE_BYTES = 1 << 20
 
     def to_device(self, packed: PackedClips):
         """(pcm, offsets, lengths) on the device; one async copy for the PCM, one for the metadata."""
@@ -278,15 +334,17 @@ class _B200ExtractorBase:
         else:
             pcm_d = torch.empty(packed.pcm.numel(), dtype=torch.float32, device=dev)
             pcm_d.copy_(packed.pcm, non_blocking=True)
-        _, meta = self._stage.get(0, 2 * B) if not packed.pcm.is_cuda else (None, torch.empty(2 * B, dtype=torch.int64, pin_memory=True))
+        meta = torch.empty(2 * B, dtype=torch.int64, pin_memory=True)     # (torch caches pinned blocks; freed in stream order)
         mv = meta.numpy()
         mv[:B] = packed.offsets
+        mv[B:2 * B] = 0
         mv[B:2 * B].view(np.int32)[:B] = packed.lengths       # lengths live in the low half of the second block
         meta_d = torch.empty(2 * B, dtype=torch.int64, device=dev)
-        meta_d.copy_(meta[:2 * B], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        self._stage.event = ev
+        meta_d.copy_(meta, non_blocking=True)
+        if packed.stage is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            packed.stage.event = ev
         offsets_d = meta_d[:B]
         lengths_d = meta_d[B:2 * B].view(torch.int32)[:B]
         return pcm_d, offsets_d, lengths_d

@@ -74,6 +74,31 @@ for name, N, M, D, ragged in (("cfg5", 4096, 4096, 768, False), ("ragged", 1000,
                      "ms_nccl_allgather_then_gemm": ms_nccl,
                      "scores_per_s_fused": N * M / (min(ms_fused, ms_mc) * 1e-3)}
     del scorer, mc
+# ---- empty shards, back to back: fewer rows than ranks on both sides, new inputs every call, no barrier in between.  A rank
+# with no local rows (no GEMM) and slots with no rows (never read by a GEMM) must still take part in the flag protocol, or a
+# fast rank's push of call e + 2 lands on planes a slow peer is still reading for call e.
+D = 96
+N, M = world - 1, max(1, world // 2)                            # the last rank has no a rows; half the ranks have no b rows
+lo_a, hi_a = scoring.shard_rows(N, world, rank)
+lo_b, hi_b = scoring.shard_rows(M, world, rank)
+counts = [scoring.shard_rows(M, world, r)[1] - scoring.shard_rows(M, world, r)[0] for r in range(world)]
+scorer = scoring.GatheredScorer(max(max(counts), 1), D, device=dev)
+calls = []
+for it in range(6):
+    a, b = synth.embedding_pairs(max(N, M), D, seed=100 + it)
+    a_loc = torch.from_numpy(a[lo_a:hi_a]).to(dev)
+    b_loc = torch.from_numpy(b[:M][lo_b:hi_b]).to(dev)
+    calls.append((a, b, scorer(a_loc, b_loc, counts=counts)))   # back to back: nothing synchronises between the calls
+    if rank % 2 == it % 2:
+        torch.cuda._sleep(2_000_000)                            # skew the ranks (about a millisecond)
+worst_empty = 0.0
+for a, b, S in calls:
+    assert tuple(S.shape) == (hi_a - lo_a, M)
+    if hi_a > lo_a:
+        worst_empty = max(worst_empty, float(np.abs(S.cpu().numpy() - OC.matrix_f64(a[lo_a:hi_a], b[:M])).max()))
+assert worst_empty <= 1e-5, (rank, worst_empty)
+results["empty_shards"] = {"N": N, "M": M, "D": D, "calls": len(calls), "max_abs_err_vs_f64": worst_empty}
+del scorer
 if rank == 0:
     print(json.dumps({"n_gpus": world, "results": results}), flush=True)
 dist.destroy_process_group()

@@ -310,3 +310,21 @@ def test_schedule_and_uniform_promise_give_identical_bits(cuda_device):
     ref, _ = OK.extract([clips[3]])
     T2 = ref.shape[1]
     assert np.abs(a[3, :T2].cpu().numpy() - ref[0]).max() <= TOL
+
+
+def test_packed_batches_do_not_share_staging_memory(fe):
+    """A PackedClips stays valid while its owner holds it: packing the next batch (or two) takes another pinned buffer, and a
+    buffer is reused only after the copies out of it have drained."""
+    batches = [synth.batch_variable(24, seed=50 + k, whole_seconds=False, max_s=3) for k in range(3)]
+    refs = [fe(b, sampling_rate=16000, return_tensors="pt")["input_features"].clone() for b in batches]
+    packed = [fe.pack(b) for b in batches]                      # three live PackedClips before any is consumed
+    assert len({p.pcm.data_ptr() for p in packed}) == 3
+    for k in (2, 0, 1):
+        got = fe(packed[k], sampling_rate=16000, return_tensors="pt")["input_features"]
+        assert torch.equal(got, refs[k])
+    again = fe(packed[0], sampling_rate=16000, return_tensors="pt", output="host")["input_features"]
+    assert torch.equal(again, refs[0].cpu())                    # a PackedClips may be consumed more than once
+    del packed
+    for _ in range(4):                                          # steady state: the pool does not grow call after call
+        fe(batches[0], sampling_rate=16000, return_tensors="pt", output="host")
+    assert len(fe._stages.stages) <= 4

@@ -26,6 +26,6 @@ def test_fused_gather_matches_oracle_and_nccl_path():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     res = json.loads(line)
-    assert res["n_gpus"] == world and set(res["results"]) == {"cfg5", "ragged", "cfg5_d1024"}
+    assert res["n_gpus"] == world and set(res["results"]) == {"cfg5", "ragged", "cfg5_d1024", "empty_shards"}
     for v in res["results"].values():
         assert v["max_abs_err_vs_f64"] <= 1e-5

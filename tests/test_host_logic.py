@@ -183,3 +183,27 @@ def test_default_resample_mode_is_the_reference_call_and_says_so_without_librosa
             proc._prepare(x, 48000)
     with pytest.raises(ValueError):
         AudioTextProcessor(device="cpu", resample="nope")
+
+
+def test_native_host_pack_gathers_ragged_segments(lib):
+    """stx_host_pack: pageable arrays -> one staging buffer, any thread count, work split by bytes (no CUDA involved)."""
+    import ctypes as C
+    import numpy as np
+    rng = np.random.default_rng(0)
+    sizes = [0, 1, 7, 1023, 262144 + 3, 5, 700001, 64]
+    clips = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    offs = np.zeros(len(sizes), np.int64)
+    np.cumsum([(n + 31) // 32 * 32 for n in sizes[:-1]], out=offs[1:])
+    total = int(offs[-1] + sizes[-1])
+    src = np.array([c.ctypes.data for c in clips], np.uint64)
+    nbytes = np.array(sizes, np.int64) * 4
+    for threads in (1, 2, 3, 8, 64):
+        dst = np.full(total + 16, np.float32(-7.0))
+        rc = lib.stx_host_pack(src.ctypes.data, nbytes.ctypes.data, dst.ctypes.data, (offs * 4).ctypes.data, len(sizes), threads)
+        assert rc == 0
+        want = np.full(total + 16, np.float32(-7.0))
+        for c, o in zip(clips, offs):
+            want[o:o + c.size] = c
+        assert np.array_equal(dst, want)                      # every byte in place, nothing outside the segments touched
+    assert lib.stx_host_pack(None, None, None, None, 0, 4) == 0
+    assert lib.stx_host_pack(None, None, None, None, 3, 4) != 0 and b"stx_host_pack" in lib.stx_last_error()
