@@ -571,17 +571,27 @@ def measure_scoring(ctx, iters=20):
     from speech_transcript_embeddings_b200 import scoring
     dev, world, rank = ctx.dev, ctx.world, ctx.rank
     res, worst = {}, 0.0
-    cases = [("cfg5_d768", 4096, 768, None), ("cfg5_d1024", 4096, 1024, None)]
+    # (name, a rows per rank, b rows per rank, D, rows of the stripe checked against float64)
+    cases = [("cfg5_d768", None, None, 768, None), ("cfg5_d1024", None, None, 1024, None)]
     if world > 1:
-        cases.append(("large_32768_d768", 32768, 768, 64))
-    for name, N, D, check_rows in cases:
-        lo, hi = scoring.shard_rows(N, world, rank)
+        # retrieval-shaped: few queries per rank against a large sharded corpus, so that the exchange (NVLink) takes about as
+        # long as the contraction and the overlap of the fused kernel has something to hide
+        cases.append(("wide_512_queries_x_32768_corpus_rows_per_rank_d768", 512, 32768, 768, 64))
+    for name, n_rank, m_rank, D, check_rows in cases:
+        if n_rank is None:
+            N = M = 4096
+            lo, hi = scoring.shard_rows(N, world, rank)
+            n_loc = m_loc = hi - lo
+            counts = [scoring.shard_rows(M, world, r)[1] - scoring.shard_rows(M, world, r)[0] for r in range(world)]
+        else:
+            n_loc, m_loc = n_rank, m_rank
+            N, M = n_rank * world, m_rank * world
+            counts = [m_rank] * world
         g = torch.Generator(device=dev).manual_seed(1000 + rank)
-        a_loc = torch.nn.functional.normalize(torch.randn(hi - lo, D, generator=g, device=dev), dim=1)
-        b_loc = torch.nn.functional.normalize(a_loc + 0.5 * torch.randn(hi - lo, D, generator=g, device=dev), dim=1)
-        counts = [scoring.shard_rows(N, world, r)[1] - scoring.shard_rows(N, world, r)[0] for r in range(world)]
-        out = torch.empty((hi - lo, N), dtype=torch.float32, device=dev)
-        entry = {"N": N, "M": N, "D": D, "rows_per_rank": hi - lo}
+        b_loc = torch.nn.functional.normalize(torch.randn(m_loc, D, generator=g, device=dev), dim=1)
+        a_loc = torch.nn.functional.normalize(b_loc[:n_loc] + 0.5 * torch.randn(n_loc, D, generator=g, device=dev), dim=1)
+        out = torch.empty((n_loc, M), dtype=torch.float32, device=dev)
+        entry = {"N": N, "M": M, "D": D, "a_rows_per_rank": n_loc, "b_rows_per_rank": m_loc}
         if world > 1:
             scorer = scoring.GatheredScorer(max(counts), D, device=dev)
             fused = lambda i: scorer(a_loc, b_loc, counts=counts, out=out)                      # noqa: E731
@@ -589,26 +599,29 @@ def measure_scoring(ctx, iters=20):
             S = fused(0)
             S_nccl = nccl(0)
             b_all = scoring.all_gather_rows(b_loc, counts=counts)
-            rows = check_rows or (hi - lo)
+            rows = min(check_rows or n_loc, n_loc)
             err = f64_stripe_err(torch, S, a_loc, b_all, rows)
             diff = float((S - S_nccl).abs().max().item())
+            del S_nccl, b_all
             entry.update({"ms_fused": ctx.timed(fused, iters, 5) / iters, "ms_nccl_allgather_then_gemm": ctx.timed(nccl, iters, 5) / iters,
                           "max_abs_err_vs_f64": ctx.max_over_ranks(err), "err_rows_checked_per_rank": rows,
                           "max_abs_diff_vs_nccl_path": ctx.max_over_ranks(diff),
-                          "push": "multicast" if scorer.multicast_ptr is not None else "unicast"})
+                          "push": "multicast" if scorer.multicast_ptr is not None else "unicast",
+                          "exchange_bytes_received_per_rank": (M - m_loc) * ((D + 63) // 64 * 64) * 4})
             entry["fused_speedup"] = entry["ms_nccl_allgather_then_gemm"] / entry["ms_fused"]
             worst = max(worst, entry["max_abs_err_vs_f64"], entry["max_abs_diff_vs_nccl_path"])
-            del scorer, b_all, S_nccl
+            del scorer
         else:
             local = lambda i: scoring.cosine_matrix(a_loc, b_loc)                                # noqa: E731
             S = local(0)
-            err = f64_stripe_err(torch, S, a_loc, b_loc, hi - lo)
+            err = f64_stripe_err(torch, S, a_loc, b_loc, n_loc)
             entry.update({"ms": ctx.timed(local, iters, 5) / iters, "max_abs_err_vs_f64": err})
-            entry["tflops_algorithmic"] = 2.0 * N * N * D / entry["ms"] / 1e9
+            entry["tflops_algorithmic"] = 2.0 * N * M * D / entry["ms"] / 1e9
             worst = max(worst, err)
-        entry["scores_per_s"] = float(N) * N / ((entry.get("ms_fused") or entry.get("ms")) * 1e-3)
+        entry["scores_per_s"] = float(N) * M / ((entry.get("ms_fused") or entry.get("ms")) * 1e-3)
         res[name] = entry
-        del out
+        del out, S
+        torch.cuda.empty_cache()
     res["worst_abs_err"] = worst
     res["tolerance"] = 1e-5
     res["ok"] = bool(worst <= 1e-5)

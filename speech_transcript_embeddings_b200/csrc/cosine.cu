@@ -161,9 +161,17 @@ c_pos_neg_loss(const float* __restrict__ per_sample, const float* __restrict__ s
 //              tcgen05.commit frees the stage), warps 2-5 = epilogue (tcgen05.ld 32x32b.x32 -> registers -> 128-byte
 //              row segments of S).  Two accumulators in TMEM (2 x 128 columns): the epilogue of tile i overlaps the
 //              main loop of tile i + 1.
-constexpr int kTM = 128, kTN = 128, kTK = 32, kStages = 3;
+// Stage geometry (A/B: tools/ab_build.py): rows of kRowBytes per k-block in shared memory.  128-byte rows (SWIZZLE_128B) give 3
+// stages of 64 KB; 64-byte rows (SWIZZLE_64B) give 7 stages of 32 KB, i.e. 192 KB instead of 128 KB of operands in flight
+// behind the stage being consumed -- with bfloat16 operands the kernel is bound by TMA latency x bandwidth, not by the tensor pipe.
+#ifndef STX_C_ROW_BYTES
+#define STX_C_ROW_BYTES 128
+#endif
+constexpr int kRowBytes = STX_C_ROW_BYTES;
+static_assert(kRowBytes == 128 || kRowBytes == 64, "k-block rows are 128 or 64 bytes");
+constexpr int kTM = 128, kTN = 128, kTK = 32, kStages = kRowBytes == 128 ? 3 : 7;
 constexpr int kTcThreads = 192;
-constexpr int kTileBytes = kTM * kTK * 4;       // one 128 x 32 float plane tile
+constexpr int kTileBytes = kTM * kRowBytes;     // one plane tile: 128 rows of one k-block
 constexpr unsigned kTmemCols = 512;             // two tiles in flight x two 128 x 128 float accumulators (hi.hi | cross terms)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 [7,10) [10,13), K-major A and B,
 // N >> 3 at [17,23), M >> 4 at [24,29)
@@ -205,8 +213,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // >> 4 at [32,46), version 1 at [46,48), layout SWIZZLE_128B = 2 at [61,64)
 __device__ __forceinline__ unsigned long long umma_desc(const void* tile, int k_bytes) {
     const unsigned addr = smem_u32(tile) + (unsigned)k_bytes;
-    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    // stride between 8-row groups: 8 x row bytes; layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    return (unsigned long long)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)((8 * kRowBytes) >> 4) << 32) |
+           (1ull << 46) | ((unsigned long long)(kRowBytes == 128 ? 2 : 4) << 61);
 }
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -493,7 +502,7 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                     } while ((int)(v - g.epoch) < 0);
                     asm volatile("fence.proxy.async;" ::: "memory");
                 }
-                const int kelems = g.bf16 ? 2 * kTK : kTK;         // elements per 128-byte k-block row
+                const int kelems = g.bf16 ? kRowBytes / 2 : kRowBytes / 4;      // elements per k-block row
                 for (int kb = 0; kb < kb_per_pass; ++kb, ++it) {
                     const int s = it % kStages, round = it / kStages;
                     if (round > 0) mbar_wait(&sm.empty[s], (unsigned)(round - 1) & 1u);
@@ -510,6 +519,13 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             int it = 0, n = 0;
+            // Descriptors of stage 0, built ONCE: the planes of a stage are kTileBytes apart and a K step is 32 bytes, so the
+            // descriptor of (stage s, step k) is the base plus s * (kTileBytes >> 4) + 2 k in its 16-byte address field.  (Built
+            // per MMA -- a generic-to-shared conversion and half a dozen dependent integer operations each, on a single thread --
+            // the issue loop took ~170 cycles per MMA and the tensor pipe waited for it: 0.097 -> see DESIGN.md.)
+            const unsigned long long ah0 = umma_desc(sm.a_hi[0], 0), al0 = umma_desc(sm.a_lo[0], 0);
+            const unsigned long long bh0 = umma_desc(sm.b_hi[0], 0), bl0 = umma_desc(sm.b_lo[0], 0);
+            const bool bf = g.bf16 != 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++n) {
                 const int acc = n & 1;
                 if (n >= 2) mbar_wait(&sm.tmem_empty[acc], (unsigned)(n / 2 - 1) & 1u);     // the epilogue has drained it
@@ -524,18 +540,21 @@ c_nxm_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUte
                     const int s = it % kStages;
                     mbar_wait(&sm.full[s], (unsigned)(it / kStages) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned long long so = (unsigned long long)(s * (kTileBytes >> 4));
+                    const unsigned long long ah = ah0 + so, al = al0 + so, bh = bh0 + so, bl = bl0 + so;
+                    if (bf) {                       // 32 bytes per K step in both formats: 16 bfloat16 or 8 TF32
 #pragma unroll
-                    for (int k = 0; k < kTK / 8; ++k) {
-                        const unsigned long long ah = umma_desc(sm.a_hi[s], k * 32), al = umma_desc(sm.a_lo[s], k * 32);
-                        const unsigned long long bh = umma_desc(sm.b_hi[s], k * 32), bl = umma_desc(sm.b_lo[s], k * 32);
-                        if (g.bf16) {               // 32 bytes per K step in both formats: 16 bfloat16 or 8 TF32
-                            umma_bf16(d, ah, bh, (kb | k) != 0);
-                            umma_bf16(dx, al, bh, (kb | k) != 0);
-                            umma_bf16(dx, ah, bl, 1);
-                        } else {
-                            umma_tf32(d, ah, bh, (kb | k) != 0);
-                            umma_tf32(dx, al, bh, (kb | k) != 0);
-                            umma_tf32(dx, ah, bl, 1);
+                        for (int k = 0; k < kRowBytes / 32; ++k) {
+                            umma_bf16(d, ah + 2 * k, bh + 2 * k, (kb | k) != 0);
+                            umma_bf16(dx, al + 2 * k, bh + 2 * k, (kb | k) != 0);
+                            umma_bf16(dx, ah + 2 * k, bl + 2 * k, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kRowBytes / 32; ++k) {
+                            umma_tf32(d, ah + 2 * k, bh + 2 * k, (kb | k) != 0);
+                            umma_tf32(dx, al + 2 * k, bh + 2 * k, (kb | k) != 0);
+                            umma_tf32(dx, ah + 2 * k, bl + 2 * k, 1);
                         }
                     }
                     umma_commit(&sm.empty[s]);      // the stage is free once these MMAs have read it
@@ -701,10 +720,11 @@ int make_map(CUtensorMap* map, const void* base, int rows, int Dp, int box_rows,
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)Dp * (bf16 ? 2 : 4)};
-    const cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * kTK : kTK), (cuuint32_t)box_rows};        // 128 bytes per box row
+    const cuuint32_t box[2] = {(cuuint32_t)(bf16 ? kRowBytes / 2 : kRowBytes / 4), (cuuint32_t)box_rows};   // kRowBytes per box row
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, kRowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return STX_EINVAL; }
     return 0;
@@ -737,7 +757,8 @@ int launch_gemm(const void* a_planes, int a_rows_total, const void* b_planes, in
     if (dev >= 0 && dev < 64 && !sms[dev]) STX_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     const long long tiles = (long long)n_col_tiles * ((g.n_rows + kTM - 1) / kTM);
     const int ctas = (int)std::min<long long>(tiles, (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148);
-    STX_LAUNCH(c_nxm_tc, dim3(ctas), dim3(kTcThreads), smem_bytes, st, ma, mb, g, Dp / (g.bf16 ? 2 * kTK : kTK), n_col_tiles, d_S);
+    STX_LAUNCH(c_nxm_tc, dim3(ctas), dim3(kTcThreads), smem_bytes, st, ma, mb, g, Dp / (g.bf16 ? kRowBytes / 2 : kRowBytes / 4),
+               n_col_tiles, d_S);
     return 0;
 }
 

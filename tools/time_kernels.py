@@ -14,11 +14,39 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from speech_transcript_embeddings_b200 import _lib, ops  # noqa: E402
 
-recipe = sys.argv[1] if len(sys.argv) > 1 else "K"
+recipe = sys.argv[1] if len(sys.argv) > 1 else "K"          # K | W | C (cosine matrix, N = M = clips * 64, D = 768)
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 secs = float(sys.argv[3]) if len(sys.argv) > 3 else 30.0
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 dev = torch.device("cuda", 0)
+if recipe == "C":
+    N = B * 64
+    g = torch.Generator(device=dev).manual_seed(0)
+    a = torch.nn.functional.normalize(torch.randn(N, 768, generator=g, device=dev), dim=1)
+    b = torch.nn.functional.normalize(a + 0.5 * torch.randn(N, 768, generator=g, device=dev), dim=1)
+    S = torch.empty((N, N), dtype=torch.float32, device=dev)
+    for _ in range(5):
+        ops.cosine_nxm(a, b, out=S)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.cosine_nxm(a, b, out=S)
+    e1.record()
+    torch.cuda.synchronize()
+    _lib.profile(True)
+    for _ in range(iters):
+        ops.cosine_nxm(a, b, out=S)
+    torch.cuda.synchronize()
+    per = {}
+    for name, ms in _lib.profile_collect():
+        per.setdefault(name, []).append(ms)
+    _lib.profile(False)
+    ref = (a[:64].double() @ b.double().T)
+    print(json.dumps({"lib": os.environ.get("STX_B200_LIB", "in-tree"), "recipe": "C", "N": N, "step_ms": round(e0.elapsed_time(e1) / iters, 5),
+                      "kernels_us": {k: round(1e3 * statistics.mean(v), 2) for k, v in per.items()},
+                      "max_abs_err_64_rows": float((S[:64].double() - ref).abs().max())}))
+    sys.exit(0)
 n = int(secs * 16000)
 pools = []
 for s in range(4):                                             # 4 batches rotated: inputs + outputs larger than L2
