@@ -74,6 +74,15 @@
                                  //    atomic per work item sit on the group's critical path).  0: every CTA of k_normalize sums the
                                  //    clip's partials itself (round 1)
 #endif
+#ifndef STX_K_CVT_SPLIT
+#define STX_K_CVT_SPLIT 0        // 1: the conversion pass of k_frames_duo widens one of its two float32 operands per sample on the
+                                 //    integer pipe (exponent re-bias + shifts) and the other with F2F, instead of both on the
+                                 //    quarter-rate XU pipe
+#endif
+#ifndef STX_K_BAR2_LATE
+#define STX_K_BAR2_LATE 0        // 1: the "H2 complete" barrier of k_frames_duo moves behind the first half of pass 2, so that the
+                                 //    shared-memory stores of the second exchange half drain under that half's FP64 work
+#endif
 #ifndef STX_K_NORM_PDL
 #define STX_K_NORM_PDL 0         // 1: k_normalize is launched as the programmatic dependent of k_frames_duo (no measurable gain:
                                  //    the frames kernel owns every SM until its last CTA retires)
@@ -192,6 +201,15 @@ __device__ __forceinline__ float power_to_f32(double p) {
     const unsigned hi = (unsigned)__double2hiint(p), lo = (unsigned)__double2loint(p);
     const unsigned h = max(hi, 0x38000000u) - 0x38000000u;
     return __uint_as_float(__funnelshift_l(lo, h, 3));
+}
+
+// float32 -> float64 on the integer pipe (exact for normal numbers: re-bias the exponent by 896, shift the mantissa).  Zeros
+// and denormals come out as values below 2^-126 instead of exactly: at most 1.2e-38 in a sample that is then scaled by <= 2^15
+// and squared, i.e. far below the mel floor -- the output bits are the same as with an exact conversion.
+__device__ __forceinline__ double f32_to_f64_int(float x) {
+    const unsigned b = __float_as_uint(x);
+    const unsigned hi = (((b >> 3) & 0x0fffffffu) + 0x38000000u) | (b & 0x80000000u);
+    return __hiloint2double((int)hi, (int)(b << 29));
 }
 
 // ---- mbarrier + 1-D bulk copy (TMA) ---------------------------------------------------------
@@ -783,7 +801,11 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                         const float* src = stage + kLead + 80 * hr + c;
                         float xm = src[-1], xi = src[0];
                         if (kPeak) { xm = xm / peak; xi = xi / peak; }
+#if STX_K_CVT_SPLIT
+                        sg.u.d[80 * hr + c + (hr >> 1)] = fma(-0.97, f32_to_f64_int(xm), (double)xi);
+#else
                         sg.u.d[80 * hr + c + (hr >> 1)] = fma(-0.97, (double)xm, (double)xi);
+#endif
                     }
                 }
             }
@@ -880,7 +902,9 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
 #pragma unroll
             for (int s = 0; s < 8; ++s) sg.ex[s][w8 + kGWarps][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
         }
+#if !STX_K_BAR2_LATE
         group_bar(g);                               // H2 complete
+#endif
 
         double c = 0.0;
         auto put = [&](int bin, double pr, double pi, double2 wh) {
@@ -906,6 +930,9 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 put(k2 < 8 ? w8 + 32 * k2 : 512 - w8 - 32 * k2, yr[k2], yi[k2], c_wh[w8][k2]);
         }
         cparity ^= 1;
+#if STX_K_BAR2_LATE
+        group_bar(g);                               // H2 complete (its stores drained under the first half's arithmetic)
+#endif
         // ---- pass 2, second half: row 8 + w8 ----
         {
             const int row = kGWarps + w8;
