@@ -88,8 +88,21 @@
                                  //    the frames kernel owns every SM until its last CTA retires)
 #endif
 
+#ifndef STX_K_TRACE
+#define STX_K_TRACE 0            // 1: thread 0 of every group of k_frames_duo adds the cycles between its group barriers to per-phase
+                                 //    counters (stx_debug_ktrace reads and clears them; tools/k_phase_trace.py)
+#endif
+
 namespace stx {
 namespace {
+
+#if STX_K_TRACE
+__device__ unsigned long long g_ktrace[16];
+__device__ __forceinline__ unsigned clock_lo() { unsigned c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); return c; }
+#define KTRACE(i) do { if (tl == 0) { const unsigned now__ = clock_lo(); sg.tacc[i] += now__ - sg.tlast; sg.tlast = now__; } } while (0)
+#else
+#define KTRACE(i) do { } while (0)
+#endif
 
 constexpr int kFrame = STX_K_FRAME;
 constexpr int kHop = STX_K_HOP;
@@ -617,6 +630,9 @@ struct SmemG {
     unsigned long long cbar;     // cval ready (one arrival per warp of the group)
     TileDesc desc[2];            // the tile in flight and the next one (written by the group's thread 0)
     int is_last;                 // this group completed the last work item of a clip (it reduces the clip's statistics)
+#if STX_K_TRACE
+    unsigned tlast, tacc[8];
+#endif
 };
 struct SmemDuo {
     SmemG g[2];
@@ -772,6 +788,10 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     unsigned long long s1 = 0, s2h = 0, s2l = 0;    // fixed-point statistics of bin tl % 80 over the rows tl / 80 + 3 i
     const int sbin = tl % kMel, srow = tl / kMel;
     unsigned parity = 0, cparity = 0;
+#if STX_K_TRACE
+    if (tl < 8) sg.tacc[tl] = 0u;
+    if (tl == 0) sg.tlast = clock_lo();
+#endif
 
     // convert(td): landed PCM of tile td -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161
     auto convert = [&](const TileDesc& td) {
@@ -801,7 +821,9 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                         const float* src = stage + kLead + 80 * hr + c;
                         float xm = src[-1], xi = src[0];
                         if (kPeak) { xm = xm / peak; xi = xi / peak; }
-#if STX_K_CVT_SPLIT
+#if STX_K_CVT_SPLIT == 2
+                        sg.u.d[80 * hr + c + (hr >> 1)] = fma(-0.97, f32_to_f64_int(xm), f32_to_f64_int(xi));
+#elif STX_K_CVT_SPLIT
                         sg.u.d[80 * hr + c + (hr >> 1)] = fma(-0.97, f32_to_f64_int(xm), (double)xi);
 #else
                         sg.u.d[80 * hr + c + (hr >> 1)] = fma(-0.97, (double)xm, (double)xi);
@@ -868,6 +890,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         pass1(w8 + kGWarps, 1);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         group_bar(g);                               // H1 complete, psum complete; d is dead, its storage becomes the power spectrum
+        KTRACE(0);
 
         // ---- c = 0.03 * mean(frame): warp w8 sums the 16 partials of frames 4 w8 .. 4 w8 + 3 ----
         {
@@ -892,6 +915,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             xr[n2] = v.x; xi[n2] = v.y;
         }
         group_bar(g);                               // H1 is in registers: the exchange buffer is free for H2
+        KTRACE(1);
         // ---- the stash comes back: rows 8..15 of both roles -> exchange (H2) ----
         {
             double hs[16];
@@ -904,6 +928,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         }
 #if !STX_K_BAR2_LATE
         group_bar(g);                               // H2 complete
+        KTRACE(2);
 #endif
 
         double c = 0.0;
@@ -950,6 +975,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 put(k2 < 8 ? row + 32 * k2 : 512 - row - 32 * k2, yr[k2], yi[k2], c_wh[row][k2]);
         }
         group_bar(g);                               // power spectrum complete; the exchange buffer is idle until the next pass 1
+        KTRACE(3);
         if (tl == 0) prefetch(sg.desc[slot ^ 1]);   // ... and takes the next tile's PCM meanwhile
 
         // ---- sparse mel + ln ----
@@ -983,6 +1009,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
 #endif
         }
         group_bar(g);
+        KTRACE(4);
 
         // ---- coalesced store of the tile's rows + statistics ----
         const TileDesc& cur = sg.desc[slot];
@@ -1061,11 +1088,15 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
       }
         if (sg.desc[slot].valid) convert(sg.desc[slot]);
         group_bar(g);                               // d ready; landing zone and staged rows consumed
+        KTRACE(6);
         first_trip = false;
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+#if STX_K_TRACE
+    if (tl < 8) atomicAdd(&g_ktrace[tl], (unsigned long long)sg.tacc[tl]);
+#endif
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(kTmemCols) : "memory");
@@ -1474,6 +1505,18 @@ inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 }  // namespace stx
 
 extern "C" {
+
+#if STX_K_TRACE
+// debug builds only (tools/k_phase_trace.py): cycles per phase summed over all groups, then cleared
+int stx_debug_ktrace(unsigned long long* host16) {
+    using namespace stx;
+    STX_CUDA(cudaDeviceSynchronize());
+    STX_CUDA(cudaMemcpyFromSymbol(host16, g_ktrace, sizeof(unsigned long long) * 16));
+    static const unsigned long long zero[16] = {0};
+    STX_CUDA(cudaMemcpyToSymbol(g_ktrace, zero, sizeof(zero)));
+    return 0;
+}
+#endif
 
 int stx_fbank_k_workspace(int B, int max_length, size_t* bytes) {
     using namespace stx;
