@@ -88,6 +88,16 @@
                                  //    the frames kernel owns every SM until its last CTA retires)
 #endif
 
+#ifndef STX_K_ILP
+#define STX_K_ILP 0              // 1: the latency-bound phases of k_frames_duo (mel, store + statistics, conversion) are written so that
+                                 //    their independent dependency chains overlap: results are kept in registers until all loads of
+                                 //    the phase have been issued (a store to shared memory in between makes ptxas serialise the
+                                 //    chains), full tiles take branch-free paths, and the conversion walks runs of consecutive
+                                 //    samples (half the float32 -> float64 conversions).  0: the round-1 forms (A/B)
+#endif
+#ifndef STX_K_SOLO
+#define STX_K_SOLO 0             // 1 (experiment): only group 0 of every CTA works
+#endif
 #ifndef STX_K_TRACE
 #define STX_K_TRACE 0            // 1: thread 0 of every group of k_frames_duo adds the cycles between its group barriers to per-phase
                                  //    counters (stx_debug_ktrace reads and clears them; tools/k_phase_trace.py)
@@ -97,11 +107,19 @@ namespace stx {
 namespace {
 
 #if STX_K_TRACE
-__device__ unsigned long long g_ktrace[16];
+__device__ unsigned long long g_ktrace[64];
 __device__ __forceinline__ unsigned clock_lo() { unsigned c; asm volatile("mov.u32 %0, %%clock;" : "=r"(c)); return c; }
+#endif
+#if STX_K_TRACE == 1
 #define KTRACE(i) do { if (tl == 0) { const unsigned now__ = clock_lo(); sg.tacc[i] += now__ - sg.tlast; sg.tlast = now__; } } while (0)
+#define KTRACE_PRE(i) do { } while (0)
+#elif STX_K_TRACE == 2
+// per-warp BUSY cycles of each phase (from the warp's release by the previous barrier to its arrival at the next one)
+#define KTRACE_PRE(i) do { if (lane == 0) sg.tw[i][w8] += clock_lo() - sg.tl[w8]; } while (0)
+#define KTRACE(i) do { if (lane == 0) sg.tl[w8] = clock_lo(); } while (0)
 #else
 #define KTRACE(i) do { } while (0)
+#define KTRACE_PRE(i) do { } while (0)
 #endif
 
 constexpr int kFrame = STX_K_FRAME;
@@ -196,7 +214,11 @@ __device__ __forceinline__ float ln_pos(float x) {
     const float e = (float)((bits >> 23) - 127);
     const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
     float l2;
+#if STX_K_ILP
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(m));     // m is in [1, 2): .ftz only removes the denormal-input fix-up code
+#else
     asm("lg2.approx.f32 %0, %1;" : "=f"(l2) : "f"(m));
+#endif
     constexpr float ln2_hi = 0.693145751953125f;          // 16 significant bits: e * ln2_hi is exact
     constexpr float ln2_lo = 1.42860682030941723212e-6f;
     constexpr float ln2 = 0.69314718055994530942f;
@@ -334,6 +356,25 @@ __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const fl
         acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
     }
     return ln_pos(fmaxf(acc0 + acc1, kMelFloor));
+}
+
+// the same filter, accumulation only (the caller applies floor + ln after ALL its filters' loads have been issued)
+template <int kSlot>
+__device__ __forceinline__ float mel_acc(const float* __restrict__ Pl, const float* __restrict__ melw,
+                                         const int* __restrict__ melfirst, int warp) {
+    constexpr int L = mel_len(kSlot);
+    const float4* w4 = reinterpret_cast<const float4*>(melw + mel_off(kSlot) + warp * L);
+    const float* pk = Pl + melfirst[16 * kSlot + warp] * kTile;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+        const float4 w = w4[q];
+        acc0 = fmaf(w.x, pk[(4 * q + 0) * kTile], acc0);
+        acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
+        acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
+        acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
+    }
+    return acc0 + acc1;
 }
 
 template <bool kPeak>
@@ -630,8 +671,10 @@ struct SmemG {
     unsigned long long cbar;     // cval ready (one arrival per warp of the group)
     TileDesc desc[2];            // the tile in flight and the next one (written by the group's thread 0)
     int is_last;                 // this group completed the last work item of a clip (it reduces the clip's statistics)
-#if STX_K_TRACE
+#if STX_K_TRACE == 1
     unsigned tlast, tacc[8];
+#elif STX_K_TRACE == 2
+    unsigned tl[8], tw[8][8];
 #endif
 };
 struct SmemDuo {
@@ -713,7 +756,11 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     // allocation, the tables and the pipeline fill are paid once per kernel instead of once per chunk (2.3 us each, 7 % of
     // the non-persistent form), and the groups never meet again after the first barrier, so they drift into complementary
     // phases on their own.
+#if STX_K_SOLO
+    const int item_step = gridDim.x;                // (experiment) group 0 does all the work, group 1 idles: phase times without a neighbour
+#else
     const int item_step = 2 * gridDim.x;
+#endif
     // (thread 0 of the group only) first tile of the work item at position `pos` of the schedule k_schedule wrote:
     // sched[0] = number of NON-EMPTY items, sched[1 + pos] = b * chunks_per_clip + chunk.  Group G takes positions G,
     // G + groups, ...: every group gets the same number of non-empty items (+- 1) however ragged the batch is
@@ -778,7 +825,11 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
     if (tl == 0) {
+#if STX_K_SOLO
+        if (g == 0) open_item(blockIdx.x, sg.desc[0]); else sg.desc[0].valid = 0;
+#else
         open_item(2 * blockIdx.x + g, sg.desc[0]);
+#endif
         prefetch(sg.desc[0]);
     }
     group_bar(g);                                   // the first descriptor is visible
@@ -788,9 +839,13 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
     unsigned long long s1 = 0, s2h = 0, s2l = 0;    // fixed-point statistics of bin tl % 80 over the rows tl / 80 + 3 i
     const int sbin = tl % kMel, srow = tl / kMel;
     unsigned parity = 0, cparity = 0;
-#if STX_K_TRACE
+#if STX_K_TRACE == 1
     if (tl < 8) sg.tacc[tl] = 0u;
     if (tl == 0) sg.tlast = clock_lo();
+#elif STX_K_TRACE == 2
+    if (tl < 64) sg.tw[tl >> 3][tl & 7] = 0u;
+    if (tl < 8) sg.tl[tl] = clock_lo();
+    group_bar(g);
 #endif
 
     // convert(td): landed PCM of tile td -> d[i] = x[i] - 0.97 x[i-1] (float64), rows of 161
@@ -810,6 +865,33 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             return v;
         };
         if (sr.lo == s0 - kLead && sr.hi == s0 + kTileSamples + 4) {
+#if STX_K_ILP
+            // whole tile landed and inside the clip.  215 threads, thread t converts the RUN of 25 consecutive samples
+            // 25 t .. 25 t + 24: x[i - 1] of one sample is x[i] of the one before, so 26 conversions (quarter-rate XU
+            // instructions) give 25 outputs instead of 50, and 26 loads instead of 50.  The odd stride keeps both the
+            // 4-byte loads and the 8-byte stores free of bank conflicts; a run crosses at most one row of d (160 + 1 pad).
+            constexpr int kRun = 25, kRunThreads = (kTileSamples + kRun - 1) / kRun;      // 215
+            if (tl < kRunThreads) {
+                const int i0 = kRun * tl;
+                const int q0 = (5 * tl) >> 5;               // = i0 / 160
+                const int bnd = kHop * (q0 + 1) - i0;             // first j of the run that lies in the next row
+                const float* src = stage + kLead + i0;
+                double* dst = sg.u.d + i0 + q0;
+                float xf[kRun + 1];
+#pragma unroll
+                for (int j = 0; j <= kRun; ++j) xf[j] = src[j - 1];    // (the last run reads up to 15 floats past the tile, inside the buffer)
+                if (kPeak) {
+#pragma unroll
+                    for (int j = 0; j <= kRun; ++j) xf[j] = xf[j] / peak;
+                }
+                double xd[kRun + 1];
+#pragma unroll
+                for (int j = 0; j <= kRun; ++j) xd[j] = (double)xf[j];
+                // (the last run writes 15 values past the tile's samples: inside d, never read)
+#pragma unroll
+                for (int j = 0; j < kRun; ++j) dst[j + (j >= bnd ? 1 : 0)] = fma(-0.97, xd[j], xd[j + 1]);
+            }
+#else
             // whole tile landed and inside the clip.  240 threads, thread (u, c) = (tl / 80, tl % 80) converts the half rows
             // u + 3 j (67 half rows of 80 samples): no division in the loop, independent iterations
             if (tl < kGStat) {
@@ -831,6 +913,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                     }
                 }
             }
+#endif
             if (tl < kTile) {
                 float xa = stage[kLead + tl * kHop + kFrame - 1], xz = stage[kLead - 1 + tl * kHop];
                 if (kPeak) { xa = xa / peak; xz = xz / peak; }
@@ -889,6 +972,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         pass1(w8, 0);
         pass1(w8 + kGWarps, 1);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        KTRACE_PRE(0);
         group_bar(g);                               // H1 complete, psum complete; d is dead, its storage becomes the power spectrum
         KTRACE(0);
 
@@ -914,6 +998,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             const double2 v = lds_v2f64(&sg.ex[w8][n2][lane]);
             xr[n2] = v.x; xi[n2] = v.y;
         }
+        KTRACE_PRE(1);
         group_bar(g);                               // H1 is in registers: the exchange buffer is free for H2
         KTRACE(1);
         // ---- the stash comes back: rows 8..15 of both roles -> exchange (H2) ----
@@ -927,6 +1012,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             for (int s = 0; s < 8; ++s) sg.ex[s][w8 + kGWarps][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
         }
 #if !STX_K_BAR2_LATE
+        KTRACE_PRE(2);
         group_bar(g);                               // H2 complete
         KTRACE(2);
 #endif
@@ -974,6 +1060,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             for (int k2 = 0; k2 < 16; ++k2)
                 put(k2 < 8 ? row + 32 * k2 : 512 - row - 32 * k2, yr[k2], yi[k2], c_wh[row][k2]);
         }
+        KTRACE_PRE(3);
         group_bar(g);                               // power spectrum complete; the exchange buffer is idle until the next pass 1
         KTRACE(3);
         if (tl == 0) prefetch(sg.desc[slot ^ 1]);   // ... and takes the next tile's PCM meanwhile
@@ -996,6 +1083,25 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 orow[wr + 48] = mel_slot_c<3>(Pl, wr);
                 orow[wr + 64] = mel_slot_c<4>(Pl, wr);
             }
+#elif STX_K_ILP
+            // all ten filters of the warp are accumulated in registers before the first result is stored: ten independent
+            // load -> FMA chains instead of ten serial ones
+            float r[10];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int wr = w8 + h * kGWarps;
+                r[5 * h + 0] = mel_acc<0>(Pl, sm.melw, sm.melfirst, wr);
+                r[5 * h + 1] = mel_acc<1>(Pl, sm.melw, sm.melfirst, wr);
+                r[5 * h + 2] = mel_acc<2>(Pl, sm.melw, sm.melfirst, wr);
+                r[5 * h + 3] = mel_acc<3>(Pl, sm.melw, sm.melfirst, wr);
+                r[5 * h + 4] = mel_acc<4>(Pl, sm.melw, sm.melfirst, wr);
+            }
+#pragma unroll
+            for (int i = 0; i < 10; ++i) r[i] = ln_pos(fmaxf(r[i], kMelFloor));
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int sl = 0; sl < 5; ++sl) orow[w8 + h * kGWarps + 16 * sl] = r[5 * h + sl];
 #else
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -1008,6 +1114,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             }
 #endif
         }
+        KTRACE_PRE(4);
         group_bar(g);
         KTRACE(4);
 
@@ -1019,6 +1126,27 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             const int rows = min(t_end - t0, kTile);
             const int keep = min(T_pad - t0, rows);           // frames >= T_pad count for the statistics but are not stored
             float* dst = out_b + (size_t)t0 * kMel + tl;
+#if STX_K_ILP
+            if (keep == kTile) {
+                // full tile, all of it stored: no per-row branches, so the 11 load -> convert -> split -> add chains overlap.
+                // Rows 30 and 31 exist for srow < 2 only: the third row group adds an exact zero instead.
+                float v[11];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) v[i] = outstage[(srow + 3 * i) * kOutRow + sbin];
+                v[10] = srow < 2 ? outstage[(srow + 30) * kOutRow + sbin] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < 10; ++i) dst[i * kGStat] = v[i];
+                if (srow < 2) dst[10 * kGStat] = v[10];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const double vd = (double)v[i];
+                    const double sq = vd * vd, hi = sq + kFixH, lo = sq - (hi - kFixH);      // all exact
+                    s1 += (unsigned long long)__double_as_longlong(vd + kFix1) - (unsigned long long)__double_as_longlong(kFix1);
+                    s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
+                    s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
+                }
+            } else
+#endif
 #pragma unroll
             for (int i = 0; i < 11; ++i) {
                 const int row = srow + 3 * i;
@@ -1087,6 +1215,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         slot ^= 1;
       }
         if (sg.desc[slot].valid) convert(sg.desc[slot]);
+        KTRACE_PRE(6);
         group_bar(g);                               // d ready; landing zone and staged rows consumed
         KTRACE(6);
         first_trip = false;
@@ -1094,8 +1223,10 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-#if STX_K_TRACE
+#if STX_K_TRACE == 1
     if (tl < 8) atomicAdd(&g_ktrace[tl], (unsigned long long)sg.tacc[tl]);
+#elif STX_K_TRACE == 2
+    if (tl < 64) atomicAdd(&g_ktrace[tl], (unsigned long long)sg.tw[tl >> 3][tl & 7]);
 #endif
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1508,11 +1639,11 @@ extern "C" {
 
 #if STX_K_TRACE
 // debug builds only (tools/k_phase_trace.py): cycles per phase summed over all groups, then cleared
-int stx_debug_ktrace(unsigned long long* host16) {
+int stx_debug_ktrace(unsigned long long* host16) {       // (64 words)
     using namespace stx;
     STX_CUDA(cudaDeviceSynchronize());
-    STX_CUDA(cudaMemcpyFromSymbol(host16, g_ktrace, sizeof(unsigned long long) * 16));
-    static const unsigned long long zero[16] = {0};
+    STX_CUDA(cudaMemcpyFromSymbol(host16, g_ktrace, sizeof(unsigned long long) * 64));
+    static const unsigned long long zero[64] = {0};
     STX_CUDA(cudaMemcpyToSymbol(g_ktrace, zero, sizeof(zero)));
     return 0;
 }
