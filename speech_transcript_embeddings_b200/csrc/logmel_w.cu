@@ -125,7 +125,7 @@ __device__ __forceinline__ float log10_pos(float x) {
     const float e = (float)((bits >> 23) - 127);
     const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
     float l2;
-    asm("lg2.approx.f32 %0, %1;" : "=f"(l2) : "f"(m));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(m));     // m is in [1, 2): .ftz only drops the denormal-input fix-up code
     constexpr float k_hi = 0.30102539062500f;             // log10(2) to 12 significant bits: e * k_hi is exact
     constexpr float k_lo = 4.6050389811952137e-6f;        // log10(2) - k_hi
     constexpr float k = 0.30102999566398120f;
@@ -248,13 +248,18 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         const StageRange sr = stage_range(g0, len, aligned);
         if (sr.hi > sr.lo) { mbar_wait(&sm.mbar, parity); parity ^= 1; }
         if (sr.lo == g0 && sr.hi == g0 + kTileSamples && peak == 1.0f) {
-            // 160 threads, one column each, row by row: no division, independent copies (unrolled)
-            if (tid < kHop) {
-                const float* src = sm.stage + tid;
-                float* dst = sm.u.xs + tid;
-#pragma unroll 11
-                for (int r = 0; r < 33; ++r) dst[kXRow * r] = src[kHop * r];
-                if (tid < kTileSamples - 33 * kHop) dst[kXRow * 33] = src[kHop * 33];
+            // all 256 threads, 21 elements each, every load issued before the first store (a store in between would make
+            // the copies wait for each other: the pass is pure latency)
+            float v[21];
+#pragma unroll
+            for (int j = 0; j < 21; ++j) {
+                const int i = tid + kThreads * j;
+                if (j < 20 || i < kTileSamples) v[j] = sm.stage[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 21; ++j) {
+                const int i = tid + kThreads * j;
+                if (j < 20 || i < kTileSamples) sm.u.xs[i + (unsigned)i / kHop] = v[j];
             }
         } else if (sr.lo == g0 && sr.hi == g0 + kTileSamples) {
 #pragma unroll 1
@@ -274,11 +279,6 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             }
         }
         __syncthreads();                            // xs ready; staging is free
-
-        if (tid == 0) {                             // the next tile (of this item or the next): descriptor, then its PCM
-            next_tile(sm.desc[slot], sm.desc[slot ^ 1]);
-            prefetch(sm.desc[slot ^ 1]);
-        }
 
         // ---- window + pass 1 (role = n2 = warp, warp + 8) ----
         // two roles per warp, written out (not a loop): `warp` is provably warp-uniform, a loop-carried role is not, and only
@@ -326,6 +326,12 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 for (int k2 = 0; k2 < 16; ++k2)
                     sm.u.P[k2 < 8 ? row + 25 * k2 : 400 - row - 25 * k2][lane] = fmaf(yr[k2], yr[k2], yi[k2] * yi[k2]);
             }
+        }
+        // the next tile (of this item or the next): descriptor, then its PCM (staging has been free since the layout pass).
+        // 13 rows over 8 warps: warps 5..7 have one row where the others have two, so the last warp has time for it
+        if (tid == kThreads - 32) {
+            next_tile(sm.desc[slot], sm.desc[slot ^ 1]);
+            prefetch(sm.desc[slot ^ 1]);
         }
         __syncthreads();
 
