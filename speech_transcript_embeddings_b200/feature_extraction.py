@@ -55,7 +55,11 @@ class BatchFeature(UserDict):
 
 def pack_threads() -> int:
     """Native threads one packing job may use: the cores this process may run on, shared between the ranks of the node
-    (torchrun exports LOCAL_WORLD_SIZE), at most 16 -- beyond that the copy is bound by host memory bandwidth."""
+    (torchrun exports LOCAL_WORLD_SIZE), at most 16 -- beyond that the copy is bound by host memory bandwidth.
+    ``STX_PACK_THREADS`` overrides it."""
+    forced = os.environ.get("STX_PACK_THREADS")
+    if forced:
+        return max(1, int(forced))
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
