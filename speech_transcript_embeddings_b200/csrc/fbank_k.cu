@@ -95,6 +95,14 @@
                                  //    chains), full tiles take branch-free paths, and the conversion walks runs of consecutive
                                  //    samples (half the float32 -> float64 conversions).  0: the round-1 forms (A/B)
 #endif
+#ifndef STX_K_POWER_F32
+#define STX_K_POWER_F32 0        // 1: the DC-corrected spectrum value is rounded to float32 (two F2F) and squared on the FP32 pipe (like
+                                 //    the reference, which rounds the spectrum to complex64 before |.|^2) instead of |.|^2 in float64
+                                 //    converted on the integer pipe: 2 FP64 + 2 XU + 2 FP32 instead of 4 FP64 + 3 ALU instructions per
+                                 //    bin.  Slower (222.3 vs 218.1 us): an F2F occupies the XU pipe of its scheduler for 8-16 cycles
+                                 //    (tools/microbench_coissue.cu), and 94 more of them per warp and tile cost more than the 64 FP64
+                                 //    instructions they replace
+#endif
 #ifndef STX_K_SOLO
 #define STX_K_SOLO 0             // 1 (experiment): only group 0 of every CTA works
 #endif
@@ -1020,7 +1028,12 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         double c = 0.0;
         auto put = [&](int bin, double pr, double pi, double2 wh) {
             const double a = fma(-c, wh.x, pr), bb = fma(-c, wh.y, pi);
+#if STX_K_POWER_F32
+            const float af = (float)a, bf = (float)bb;
+            sg.u.P[bin][lane] = fmaf(af, af, bf * bf);
+#else
             sg.u.P[bin][lane] = power_to_f32(fma(a, a, bb * bb));
+#endif
         };
         if (w8 == 0) {
             double e0r[7], e0i[7], e16r[8], e16i[8];
