@@ -89,11 +89,18 @@
 #endif
 
 #ifndef STX_K_ILP
-#define STX_K_ILP 0              // 1: the latency-bound phases of k_frames_duo (mel, store + statistics, conversion) are written so that
-                                 //    their independent dependency chains overlap: results are kept in registers until all loads of
-                                 //    the phase have been issued (a store to shared memory in between makes ptxas serialise the
-                                 //    chains), full tiles take branch-free paths, and the conversion walks runs of consecutive
-                                 //    samples (half the float32 -> float64 conversions).  0: the round-1 forms (A/B)
+#define STX_K_ILP 3              // bit mask over the phases of k_frames_duo that are bound by latency, not by a pipe (cfg2, us per launch):
+                                 //   1  mel: all ten filters of a warp are accumulated in registers before the first result is stored
+                                 //      (a shared-memory store between two filters makes ptxas serialise their load -> FMA chains),
+                                 //      lg2.approx.ftz (drops the denormal fix-up code)                         218.8 -> 216.2
+                                 //   2  store + statistics: full tiles take a branch-free path, so the 11 load -> convert -> split ->
+                                 //      add chains of a thread overlap instead of running as 11 guarded blocks   218.8 -> 212.6
+                                 //   4  conversion: runs of 25 consecutive samples per thread (26 float32 -> float64 conversions for
+                                 //      25 outputs instead of 50).  SLOWER (226.4): not adopted
+                                 //   3 = 1 + 2 (shipped)                                                         218.8 -> 209.6
+#endif
+#ifndef STX_K_CVT_ROWS
+#define STX_K_CVT_ROWS 0         // 1: the conversion pass of k_frames_duo walks whole rows with 160 threads (constant strides)
 #endif
 #ifndef STX_K_POWER_F32
 #define STX_K_POWER_F32 0        // 1: the DC-corrected spectrum value is rounded to float32 (two F2F) and squared on the FP32 pipe (like
@@ -222,7 +229,7 @@ __device__ __forceinline__ float ln_pos(float x) {
     const float e = (float)((bits >> 23) - 127);
     const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
     float l2;
-#if STX_K_ILP
+#if (STX_K_ILP & 1)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(m));     // m is in [1, 2): .ftz only removes the denormal-input fix-up code
 #else
     asm("lg2.approx.f32 %0, %1;" : "=f"(l2) : "f"(m));
@@ -873,7 +880,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             return v;
         };
         if (sr.lo == s0 - kLead && sr.hi == s0 + kTileSamples + 4) {
-#if STX_K_ILP
+#if (STX_K_ILP & 4)
             // whole tile landed and inside the clip.  215 threads, thread t converts the RUN of 25 consecutive samples
             // 25 t .. 25 t + 24: x[i - 1] of one sample is x[i] of the one before, so 26 conversions (quarter-rate XU
             // instructions) give 25 outputs instead of 50, and 26 loads instead of 50.  The odd stride keeps both the
@@ -899,6 +906,29 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
 #pragma unroll
                 for (int j = 0; j < kRun; ++j) dst[j + (j >= bnd ? 1 : 0)] = fma(-0.97, xd[j], xd[j + 1]);
             }
+#elif STX_K_CVT_ROWS
+            // whole tile landed and inside the clip.  160 threads, one column of the 34 rows of d each: both addresses are
+            // base + constant * row, so an iteration is 2 LDS + 2 F2F + DFMA + STS and nothing else (the half-row form below
+            // spends as many integer instructions on its addresses as on the conversion); the last warp, otherwise idle in
+            // this phase, computes xb
+            if (tl < kHop) {
+                const float* src = stage + kLead + tl;
+                double* dst = sg.u.d + tl;
+#pragma unroll
+                for (int r = 0; r < 34; ++r) {
+                    if (r < 33 || tl < kTileSamples - 33 * kHop) {
+                        float xm = src[kHop * r - 1], xi = src[kHop * r];
+                        if (kPeak) { xm = xm / peak; xi = xi / peak; }
+                        dst[kDRow * r] = fma(-0.97, (double)xm, (double)xi);
+                    }
+                }
+            }
+            if (tl >= kGThreads - kTile) {
+                const int f = tl - (kGThreads - kTile);
+                float xa = stage[kLead + f * kHop + kFrame - 1], xz = stage[kLead - 1 + f * kHop];
+                if (kPeak) { xa = xa / peak; xz = xz / peak; }
+                sg.xb[f] = 0.97 * ((double)xa - (double)xz);
+            }
 #else
             // whole tile landed and inside the clip.  240 threads, thread (u, c) = (tl / 80, tl % 80) converts the half rows
             // u + 3 j (67 half rows of 80 samples): no division in the loop, independent iterations
@@ -922,11 +952,13 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 }
             }
 #endif
+#if !STX_K_CVT_ROWS || (STX_K_ILP & 4)
             if (tl < kTile) {
                 float xa = stage[kLead + tl * kHop + kFrame - 1], xz = stage[kLead - 1 + tl * kHop];
                 if (kPeak) { xa = xa / peak; xz = xz / peak; }
                 sg.xb[tl] = 0.97 * ((double)xa - (double)xz);
             }
+#endif
         } else {
 #pragma unroll 1
             for (int i = tl; i < kTileSamples; i += kGThreads)
@@ -1096,7 +1128,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 orow[wr + 48] = mel_slot_c<3>(Pl, wr);
                 orow[wr + 64] = mel_slot_c<4>(Pl, wr);
             }
-#elif STX_K_ILP
+#elif (STX_K_ILP & 1)
             // all ten filters of the warp are accumulated in registers before the first result is stored: ten independent
             // load -> FMA chains instead of ten serial ones
             float r[10];
@@ -1139,7 +1171,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             const int rows = min(t_end - t0, kTile);
             const int keep = min(T_pad - t0, rows);           // frames >= T_pad count for the statistics but are not stored
             float* dst = out_b + (size_t)t0 * kMel + tl;
-#if STX_K_ILP
+#if (STX_K_ILP & 2)
             if (keep == kTile) {
                 // full tile, all of it stored: no per-row branches, so the 11 load -> convert -> split -> add chains overlap.
                 // Rows 30 and 31 exist for srow < 2 only: the third row group adds an exact zero instead.
