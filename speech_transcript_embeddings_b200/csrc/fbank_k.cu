@@ -99,6 +99,9 @@
                                  //      25 outputs instead of 50).  SLOWER (226.4): not adopted
                                  //   3 = 1 + 2 (shipped)                                                         218.8 -> 209.6
 #endif
+#ifndef STX_K_CVT_LINEAR
+#define STX_K_CVT_LINEAR 1       // 1: the conversion pass addresses its 23 half rows as base + constant (see there); 0: round-1 form
+#endif
 #ifndef STX_K_CVT_ROWS
 #define STX_K_CVT_ROWS 0         // 1: the conversion pass of k_frames_duo walks whole rows with 160 threads (constant strides)
 #endif
@@ -932,6 +935,30 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
 #else
             // whole tile landed and inside the clip.  240 threads, thread (u, c) = (tl / 80, tl % 80) converts the half rows
             // u + 3 j (67 half rows of 80 samples): no division in the loop, independent iterations
+#if STX_K_CVT_LINEAR
+            // ... with every address a per-thread base plus a compile-time constant: half row hr = u + 3 j sits at
+            // d[80 hr + (hr >> 1) + c], and (u + 3 j) >> 1 is linear in j once even and odd j are taken apart
+            // (j = 2 m: 3 m + (u >> 1); j = 2 m + 1: 3 m + ((u + 3) >> 1)), so the loop body is 2 LDS + 2 F2F + DFMA + STS
+            if (tl < kGStat) {
+                const int u = tl / 80, c = tl - u * 80;
+                const float* src = stage + kLead + 80 * u + c;
+                double* de = sg.u.d + 80 * u + c + (u >> 1);                       // j even
+                double* dq = sg.u.d + 80 * (u + 3) + c + ((u + 3) >> 1);           // j odd
+#pragma unroll
+                for (int m = 0; m < 12; ++m) {
+                    {
+                        float xm = src[480 * m - 1], xi = src[480 * m];
+                        if (kPeak) { xm = xm / peak; xi = xi / peak; }
+                        if (m < 11 || u == 0) de[483 * m] = fma(-0.97, (double)xm, (double)xi);      // (j = 22: half row 66 only)
+                    }
+                    if (m < 11) {
+                        float xm = src[480 * m + 240 - 1], xi = src[480 * m + 240];
+                        if (kPeak) { xm = xm / peak; xi = xi / peak; }
+                        dq[483 * m] = fma(-0.97, (double)xm, (double)xi);
+                    }
+                }
+            }
+#else
             if (tl < kGStat) {
                 const int u = tl / 80, c = tl - u * 80;
 #pragma unroll
@@ -951,6 +978,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                     }
                 }
             }
+#endif
 #endif
 #if !STX_K_CVT_ROWS || (STX_K_ILP & 4)
             if (tl < kTile) {
