@@ -164,7 +164,10 @@ __device__ __forceinline__ float max_unkey(unsigned k) {
 // blockIdx.x + gridDim.x, ...: tables, barrier initialisation and the pipeline fill are paid once per kernel instead of
 // once per chunk (1.5 us each, 9 % of the non-persistent form), and the PCM of an item's first tile lands while the
 // previous item's last tile is transformed.
-__global__ void __launch_bounds__(kThreads, 2)
+// Launch bound of THREE CTAs per SM although shared memory admits two: at the 80 registers that bound implies ptxas reads the
+// per-role window / twiddle tables through the uniform datapath (84 LDCU, no spills); at 126 registers it reads them with
+// register-indexed LDCs, which queue in the MIO behind the shared-memory traffic (the two hottest lines of the round-1 kernel).
+__global__ void __launch_bounds__(kThreads, 3)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
          const float* __restrict__ peaks, const WTables* __restrict__ tab, int B, int n_samples, int chunk_frames,
          int chunks_per_clip, float* __restrict__ out, unsigned* __restrict__ clip_max) {
