@@ -99,6 +99,9 @@
                                  //      25 outputs instead of 50).  SLOWER (226.4): not adopted
                                  //   3 = 1 + 2 (shipped)                                                         218.8 -> 209.6
 #endif
+#ifndef STX_K_NORM_COLS
+#define STX_K_NORM_COLS 1        // 1: k_normalize's threads own a column quad each (statistics in registers, no division); 0: round 1
+#endif
 #ifndef STX_K_CVT_LINEAR
 #define STX_K_CVT_LINEAR 1       // 1: the conversion pass addresses its 23 half rows as base + constant (see there); 0: round-1 form
 #endif
@@ -1414,6 +1417,39 @@ k_normalize(const int* __restrict__ lengths, const long long* __restrict__ parti
     __syncthreads();
     const int quads = T_pad * (kMel / 4);
     float4* o4 = reinterpret_cast<float4*>(out + (size_t)b * T_pad * kMel);
+#if STX_K_NORM_COLS
+    // 240 of the 256 threads: thread i owns the column quad i % 20 of the rows blockIdx.x * 12 + i / 20 + k * gridDim.x * 12, so
+    // its mean / 1/std words stay in registers and the loop has neither shared-memory reads nor a division; consecutive threads
+    // still touch consecutive float4s (a row is 20 of them)
+    if (threadIdx.x < 240) {
+        const int m = (threadIdx.x % (kMel / 4)) * 4;
+        float4 mh = make_float4(0.f, 0.f, 0.f, 0.f), ml = mh, rs = mh;
+        if (normalize && T > 0) {
+            mh = *reinterpret_cast<const float4*>(&s_mean_hi[m]);
+            ml = *reinterpret_cast<const float4*>(&s_mean_lo[m]);
+            rs = *reinterpret_cast<const float4*>(&s_rstd_f[m]);
+        }
+        const int row_step = gridDim.x * 12;
+        int t = blockIdx.x * 12 + threadIdx.x / (kMel / 4);
+        for (int q = blockIdx.x * 240 + threadIdx.x; q < quads; q += gridDim.x * 240, t += row_step) {
+            float4 v;
+            if (t < T) {
+                if (!normalize) continue;
+                v = o4[q];
+                // float32 with a two-word mean: (x - mean_hi) is exact or nearly so (same binade), mean_lo restores the bits the
+                // float32 mean lost, and the float32 1/std costs 6e-8 of a result of magnitude <= 10: |error| < 1e-6
+                v.x = ((v.x - mh.x) - ml.x) * rs.x;
+                v.y = ((v.y - mh.y) - ml.y) * rs.y;
+                v.z = ((v.z - mh.z) - ml.z) * rs.z;
+                v.w = ((v.w - mh.w) - ml.w) * rs.w;
+            } else {
+                const float f = t < T2 ? padding_value : tail_value;
+                v = make_float4(f, f, f, f);
+            }
+            o4[q] = v;
+        }
+    }
+#else
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
         const int t = q / (kMel / 4), m = (q - t * (kMel / 4)) * 4;
         float4 v;
@@ -1436,6 +1472,7 @@ k_normalize(const int* __restrict__ lengths, const long long* __restrict__ parti
         }
         o4[q] = v;
     }
+#endif
     if (mask) {
         const int rows = T_pad / 2;
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < rows; j += gridDim.x * blockDim.x) {
@@ -1816,7 +1853,8 @@ static int fbank_k_impl(const float* d_pcm, const int64_t* d_offsets, const int3
     const int quads = T_pad * (kMel / 4);
     // every CTA pays a ~2 us prologue (partials -> mean, 1/std), so the grid is ONE wave of 8 CTAs per SM, not more
     // (cfg2: 64 x 16 CTAs 20.9 us, 64 x 64 CTAs 24.9 us), and never more CTAs than 256-thread groups of float4s
-    const int gx = std::max(1, std::min((quads + 255) / 256, std::max(1, (8 * sms) / B)));
+    int gx = std::max(1, std::min((quads + 255) / 256, std::max(1, (8 * sms) / B)));
+    if (const char* e = std::getenv("STX_KN_GX")) { const int v = std::atoi(e); if (v > 0) gx = v; }     // development: CTAs per clip
 #if STX_K_NORM_PDL
     if (duo)
         return launch_dependent("k_normalize", k_normalize, dim3(gx, B), dim3(256), 0, st, d_lengths, (const long long*)partials,
