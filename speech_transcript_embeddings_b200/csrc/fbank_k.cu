@@ -99,6 +99,9 @@
                                  //      25 outputs instead of 50).  SLOWER (226.4): not adopted
                                  //   3 = 1 + 2 (shipped)                                                         218.8 -> 209.6
 #endif
+#ifndef STX_K_STASH_PAIRS
+#define STX_K_STASH_PAIRS 1      // 1: the tensor-memory stash is written one double per tcgen05.st (.x2) instead of one .x32
+#endif
 #ifndef STX_K_NORM_COLS
 #define STX_K_NORM_COLS 1        // 1: k_normalize's threads own a column quad each (statistics in registers, no division); 0: round 1
 #endif
@@ -722,6 +725,20 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const double (&v)[16])
                     "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
                     "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
+// the same stash, one double (= one natural register pair) per instruction: no moves to marshal 32 consecutive registers
+__device__ __forceinline__ void tmem_st16_pairs(unsigned taddr, const double (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                     :: "r"(taddr + 2u * i), "r"((unsigned)__double2loint(v[i])), "r"((unsigned)__double2hiint(v[i])) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_quads(unsigned taddr, const double (&v)[16]) {      // (one complex value per instruction)
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(taddr + 4u * i), "r"((unsigned)__double2loint(v[2 * i])), "r"((unsigned)__double2hiint(v[2 * i])),
+                        "r"((unsigned)__double2loint(v[2 * i + 1])), "r"((unsigned)__double2hiint(v[2 * i + 1])) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, double (&v)[16]) {
     unsigned r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -1038,7 +1055,13 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 hs[2 * (k1 - 8)] = fma(re[k1], t.x, -(im[k1] * t.y));
                 hs[2 * (k1 - 8) + 1] = fma(re[k1], t.y, im[k1] * t.x);
             }
+#if STX_K_STASH_PAIRS == 2
+            tmem_st16_quads(tstash + (unsigned)(which * 32), hs);
+#elif STX_K_STASH_PAIRS
+            tmem_st16_pairs(tstash + (unsigned)(which * 32), hs);
+#else
             tmem_st16(tstash + (unsigned)(which * 32), hs);
+#endif
         };
         pass1(w8, 0);
         pass1(w8 + kGWarps, 1);
