@@ -99,6 +99,13 @@
                                  //      25 outputs instead of 50).  SLOWER (226.4): not adopted
                                  //   3 = 1 + 2 (shipped)                                                         218.8 -> 209.6
 #endif
+#ifndef STX_K_POW_PRESCALE
+#define STX_K_POW_PRESCALE 1     // 1: the window table carries an extra factor 2^-448 (exact), so that the power spectrum comes out
+                                 //    scaled by 2^-896 and its float64 exponent field IS the float32 exponent field of the unscaled
+                                 //    value: the conversion on the integer pipe is one funnel shift instead of clamp + re-bias +
+                                 //    shift (64 instructions per warp and tile).  (Float64 transform only: forced off in the
+                                 //    float32 builds of the precision study.)
+#endif
 #ifndef STX_K_STASH_PAIRS
 #define STX_K_STASH_PAIRS 1      // 1: the tensor-memory stash is written one double per tcgen05.st (.x2) instead of one .x32
 #endif
@@ -258,8 +265,14 @@ __device__ __forceinline__ float ln_pos(float x) {
 __device__ __forceinline__ float power_to_f32(float p) { return p; }
 __device__ __forceinline__ float power_to_f32(double p) {
     const unsigned hi = (unsigned)__double2hiint(p), lo = (unsigned)__double2loint(p);
+#if STX_K_POW_PRESCALE && !STX_K_P1_F32 && !STX_K_P2_F32
+    // p is the power scaled by 2^-896 (see kWinScale): exponent field = float32's, anything below 2^-126 is a float64 denormal
+    // or zero and becomes a float32 denormal <= 7 * 2^-149 or zero by itself
+    return __uint_as_float(__funnelshift_l(lo, hi, 3));
+#else
     const unsigned h = max(hi, 0x38000000u) - 0x38000000u;
     return __uint_as_float(__funnelshift_l(lo, h, 3));
+#endif
 }
 
 // float32 -> float64 on the integer pipe (exact for normal numbers: re-bias the exponent by 896, shift the mantissa).  Zeros
@@ -1615,9 +1628,14 @@ int get_tables(const KTables** out) {
         // constant-bank tables; FFT512 of the scaled window by direct summation in long double
         static double win[16][25];
         static double2 tw[16][16], wh[16][16];
+#if STX_K_POW_PRESCALE && !STX_K_P1_F32 && !STX_K_P2_F32
+        const double kWinScale = std::ldexp(32768.0, -448);     // 2^15 (Kaldi's int16 scale) * 2^-448 (see STX_K_POW_PRESCALE)
+#else
+        const double kWinScale = 32768.0;
+#endif
         for (int n2 = 0; n2 < 16; ++n2)
             for (int n1 = 0; n1 < 25; ++n1) {
-                win[n2][n1] = w[16 * n1 + n2] * 32768.0;
+                win[n2][n1] = w[16 * n1 + n2] * kWinScale;
             }
         for (int n2 = 0; n2 < 16; ++n2)
             for (int k1 = 0; k1 < 16; ++k1) {
@@ -1631,7 +1649,7 @@ int get_tables(const KTables** out) {
                 re += (long double)(w[i] * 32768.0) * cosl(ang);
                 im += (long double)(w[i] * 32768.0) * sinl(ang);
             }
-            return make_double2((double)re, (double)im);
+            return make_double2((double)re * (kWinScale / 32768.0), (double)im * (kWinScale / 32768.0));
         };
         for (int k1 = 0; k1 < 16; ++k1)
             for (int k2 = 0; k2 < 16; ++k2) wh[k1][k2] = what(k1 + 32 * k2);
