@@ -99,12 +99,6 @@
                                  //      25 outputs instead of 50).  SLOWER (226.4): not adopted
                                  //   3 = 1 + 2 (shipped)                                                         218.8 -> 209.6
 #endif
-#ifndef STX_K_STAT_ICVT
-#define STX_K_STAT_ICVT 0
-#endif
-#ifndef STX_K_MEL_FIRST_CONST
-#define STX_K_MEL_FIRST_CONST 0  // 1: the first bin of each mel filter comes from the constant bank (weights stay in shared memory)
-#endif
 #ifndef STX_K_POW_PRESCALE
 #define STX_K_POW_PRESCALE 1     // 1: the window table carries an extra factor 2^-448 (exact), so that the power spectrum comes out
                                  //    scaled by 2^-896 and its float64 exponent field IS the float32 exponent field of the unscaled
@@ -407,11 +401,7 @@ __device__ __forceinline__ float mel_acc(const float* __restrict__ Pl, const flo
                                          const int* __restrict__ melfirst, int warp) {
     constexpr int L = mel_len(kSlot);
     const float4* w4 = reinterpret_cast<const float4*>(melw + mel_off(kSlot) + warp * L);
-#if STX_K_MEL_FIRST_CONST
-    const float* pk = Pl + c_melfirst[16 * kSlot + warp] * kTile;      // (warp-uniform: a uniform constant load, address in uniform registers)
-#else
     const float* pk = Pl + melfirst[16 * kSlot + warp] * kTile;
-#endif
     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
     for (int q = 0; q < L / 4; ++q) {
@@ -1261,11 +1251,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 if (srow < 2) dst[10 * kGStat] = v[10];
 #pragma unroll
                 for (int i = 0; i < 11; ++i) {
-#if STX_K_STAT_ICVT
-                    const double vd = f32_to_f64_int(v[i]);     // (a log-mel value is never a denormal; the padding zero maps to 2^-127: no)
-#else
                     const double vd = (double)v[i];
-#endif
                     const double sq = vd * vd, hi = sq + kFixH, lo = sq - (hi - kFixH);      // all exact
                     s1 += (unsigned long long)__double_as_longlong(vd + kFix1) - (unsigned long long)__double_as_longlong(kFix1);
                     s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
