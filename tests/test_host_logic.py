@@ -207,3 +207,18 @@ def test_native_host_pack_gathers_ragged_segments(lib):
         assert np.array_equal(dst, want)                      # every byte in place, nothing outside the segments touched
     assert lib.stx_host_pack(None, None, None, None, 0, 4) == 0
     assert lib.stx_host_pack(None, None, None, None, 3, 4) != 0 and b"stx_host_pack" in lib.stx_last_error()
+
+
+def test_pack_threads_shares_the_cores_between_ranks(monkeypatch):
+    """Native packing threads per rank: the cores of the process divided by the ranks of the node (torchrun exports
+    LOCAL_WORLD_SIZE), at most 16; STX_PACK_THREADS overrides it (tools/bench_e2e_pageable.py sweeps it)."""
+    import os
+    from speech_transcript_embeddings_b200 import feature_extraction as fx
+    cores = len(os.sched_getaffinity(0))
+    monkeypatch.delenv("STX_PACK_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert fx.pack_threads() == max(1, min(16, cores))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert fx.pack_threads() == max(1, min(16, cores // 8))
+    monkeypatch.setenv("STX_PACK_THREADS", "3")
+    assert fx.pack_threads() == 3
