@@ -168,7 +168,8 @@ class AudioTextProcessor:
             audio_array = librosa.resample(np.asarray(audio_array), orig_sr=orig_sr, target_sr=self.sampling_rate)
         # NB the reference takes the peak over the untrimmed clip (R/processor.py:91-97); so do we:
         # the trim happens on the device through the per-clip lengths
-        return np.ascontiguousarray(np.asarray(audio_array).astype(np.float32).reshape(-1))
+        # (float32 input is not copied here: the array is only read, by the packer)
+        return np.ascontiguousarray(np.asarray(audio_array).astype(np.float32, copy=False).reshape(-1))
 
     def process_audio_array(self, audio_array, orig_sr):
         return self.process_audio_batch([audio_array], orig_sr)
