@@ -126,6 +126,12 @@
                                  //    (tools/microbench_coissue.cu), and 94 more of them per warp and tile cost more than the 64 FP64
                                  //    instructions they replace
 #endif
+#ifndef STX_K_MEL_EXACT
+#define STX_K_MEL_EXACT 1        // 1 (shipped): the mel stage of k_frames_duo walks ten half slots of 8 filters (one per warp of a
+                                 //    group) whose lengths are the longest filter of the half slot (2, 3, 3, 4, 5, 6, 8, 10, 13, 16
+                                 //    bins: 560 bin reads and FMAs per frame) instead of five slots of 16 padded to 4, 4, 8, 12, 16
+                                 //    (704): 206.4 -> 201.4 us on cfg2, bit-identical (the dropped products had zero weights)
+#endif
 #ifndef STX_K_SOLO
 #define STX_K_SOLO 0             // 1 (experiment): only group 0 of every CTA works
 #endif
@@ -182,6 +188,15 @@ constexpr int kStatWords = 3 * kMel;             // per chunk: sum x | sum x^2 h
 __host__ __device__ constexpr int mel_len(int slot) { return slot == 0 ? 4 : slot == 1 ? 4 : slot == 2 ? 8 : slot == 3 ? 12 : 16; }
 __host__ __device__ constexpr int mel_off(int slot) { return slot == 0 ? 0 : mel_off(slot - 1) + 16 * mel_len(slot - 1); }
 constexpr int kMelWeights = mel_off(5);          // 704
+// (STX_K_MEL_EXACT) half slot j holds mel bins 8 j .. 8 j + 7 (one per warp of a group): mel_len10 bins are read, the weights are
+// stored padded to a multiple of four (aligned float4 loads)
+__host__ __device__ constexpr int mel_len10(int j) {
+    return j == 0 ? 2 : j == 1 ? 3 : j == 2 ? 3 : j == 3 ? 4 : j == 4 ? 5 : j == 5 ? 6 : j == 6 ? 8 : j == 7 ? 10 : j == 8 ? 13 : 16;
+}
+__host__ __device__ constexpr int mel_pad10(int j) { return (mel_len10(j) + 3) & ~3; }
+__host__ __device__ constexpr int mel_off10(int j) { return j == 0 ? 0 : mel_off10(j - 1) + 8 * mel_pad10(j - 1); }
+constexpr int kMelWeights10 = mel_off10(10);     // 672
+static_assert(kMelWeights10 <= kMelWeights, "the half-slot table fits the shared-memory array of the slot table");
 
 // warp-uniform tables (constant bank)
 __constant__ double  c_win[16][25];              // [n2][n1] = W[16 n1 + n2], W = 2^15 * Povey
@@ -191,6 +206,8 @@ __constant__ double2 c_wh[16][16];               // [k1][k2] = FFT512(W)[k1 + 32
 struct KTables {
     float melw[kMelWeights];     // [slot][warp][mel_len(slot)]
     int   melfirst[kMel];        // first FFT bin of the padded filter of mel bin m
+    float melw10[kMelWeights];   // (STX_K_MEL_EXACT) [half slot][warp of a group][mel_pad10(half slot)]
+    int   melfirst10[kMel];
 };
 
 // Precision study (north_star: "the choice evidenced by ncu"; profiles/r02_k_precision.md).  The single-group kernel k_frames
@@ -396,6 +413,23 @@ __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const fl
 }
 
 // the same filter, accumulation only (the caller applies floor + ln after ALL its filters' loads have been issued)
+template <int kHalfSlot>
+__device__ __forceinline__ float mel_acc10(const float* __restrict__ Pl, const float* __restrict__ melw,
+                                           const int* __restrict__ melfirst, int w8) {
+    constexpr int L = mel_len10(kHalfSlot), PAD = mel_pad10(kHalfSlot);
+    const float4* w4 = reinterpret_cast<const float4*>(melw + mel_off10(kHalfSlot) + w8 * PAD);
+    const float* pk = Pl + melfirst[8 * kHalfSlot + w8] * kTile;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < PAD / 4; ++q) {
+        const float4 w = w4[q];
+        if (4 * q + 0 < L) acc0 = fmaf(w.x, pk[(4 * q + 0) * kTile], acc0);
+        if (4 * q + 1 < L) acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
+        if (4 * q + 2 < L) acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
+        if (4 * q + 3 < L) acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
+    }
+    return acc0 + acc1;
+}
 template <int kSlot>
 __device__ __forceinline__ float mel_acc(const float* __restrict__ Pl, const float* __restrict__ melw,
                                          const int* __restrict__ melfirst, int warp) {
@@ -862,7 +896,10 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-#if STX_K_MEL_GEN == 0
+#if STX_K_MEL_GEN == 0 && STX_K_MEL_EXACT
+    for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw10[i];
+    if (tid < kMel) sm.melfirst[tid] = tab->melfirst10[tid];
+#elif STX_K_MEL_GEN == 0
     for (int i = tid; i < kMelWeights; i += kThreads) sm.melw[i] = tab->melw[i];
     if (tid < kMel) sm.melfirst[tid] = tab->melfirst[tid];
 #endif
@@ -1199,6 +1236,19 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             // all ten filters of the warp are accumulated in registers before the first result is stored: ten independent
             // load -> FMA chains instead of ten serial ones
             float r[10];
+#if STX_K_MEL_EXACT
+            // mel bin w8 + 8 h + 16 s = bin w8 of half slot 2 s + h
+            r[0] = mel_acc10<0>(Pl, sm.melw, sm.melfirst, w8);
+            r[1] = mel_acc10<2>(Pl, sm.melw, sm.melfirst, w8);
+            r[2] = mel_acc10<4>(Pl, sm.melw, sm.melfirst, w8);
+            r[3] = mel_acc10<6>(Pl, sm.melw, sm.melfirst, w8);
+            r[4] = mel_acc10<8>(Pl, sm.melw, sm.melfirst, w8);
+            r[5] = mel_acc10<1>(Pl, sm.melw, sm.melfirst, w8);
+            r[6] = mel_acc10<3>(Pl, sm.melw, sm.melfirst, w8);
+            r[7] = mel_acc10<5>(Pl, sm.melw, sm.melfirst, w8);
+            r[8] = mel_acc10<7>(Pl, sm.melw, sm.melfirst, w8);
+            r[9] = mel_acc10<9>(Pl, sm.melw, sm.melfirst, w8);
+#else
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int wr = w8 + h * kGWarps;
@@ -1208,6 +1258,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                 r[5 * h + 3] = mel_acc<3>(Pl, sm.melw, sm.melfirst, wr);
                 r[5 * h + 4] = mel_acc<4>(Pl, sm.melw, sm.melfirst, wr);
             }
+#endif
 #pragma unroll
             for (int i = 0; i < 10; ++i) r[i] = ln_pos(fmaxf(r[i], kMelFloor));
 #pragma unroll
@@ -1684,6 +1735,18 @@ int get_tables(const KTables** out) {
             if (lo + L > 256) lo = 256 - L;
             h.melfirst[m] = lo;
             for (int q = 0; q < L; ++q) h.melw[mel_off(slot) + wrp * L + q] = float(fb[size_t(lo + q) * kMel + m]);
+        }
+        // the same filters in half slots of 8 (STX_K_MEL_EXACT): mel_len10 bins read, weights padded to a multiple of four
+        for (int i = 0; i < kMelWeights; ++i) h.melw10[i] = 0.0f;
+        for (int m = 0; m < kMel; ++m) {
+            const int j = m / 8, w8 = m % 8, L = mel_len10(j), PAD = mel_pad10(j);
+            int lo = -1, hi = -1;
+            for (int k = 0; k <= STX_K_NFFT / 2; ++k)
+                if (fb[size_t(k) * kMel + m] != 0.0) { if (lo < 0) lo = k; hi = k; }
+            if (lo < 0 || hi - lo + 1 > L || hi > 255) { set_error("mel filter %d does not fit its half slot", m); return STX_EINVAL; }
+            if (lo + L > 256) lo = 256 - L;
+            h.melfirst10[m] = lo;
+            for (int q = 0; q < L; ++q) h.melw10[mel_off10(j) + w8 * PAD + q] = float(fb[size_t(lo + q) * kMel + m]);
         }
         // the generated mel stage (mel_k.cuh) carries its weights as immediates: they must be this library's table
         {
