@@ -49,6 +49,20 @@ constexpr int kXBuf = 34 * kXRow;
 __host__ __device__ constexpr int mel_len(int slot) { return slot < 3 ? 4 : slot == 3 ? 8 : 16; }
 __host__ __device__ constexpr int mel_off(int slot) { return slot == 0 ? 0 : mel_off(slot - 1) + 16 * mel_len(slot - 1); }
 constexpr int kMelWeights = mel_off(5);  // 576
+#ifndef STX_W_MEL_EXACT
+#define STX_W_MEL_EXACT 1               // 1 (shipped): the mel stage walks ten half slots of 8 filters (one per warp) whose lengths are
+                                        //    the longest filter of the half slot (2, 2, 2, 2, 4, 4, 6, 8, 11, 14 bins: 440 bin reads and
+                                        //    FMAs per frame) instead of five slots of 16 padded to 4, 4, 4, 8, 16 (576); the dropped
+                                        //    products had zero weights, so the results are bit-identical
+#endif
+// half slot j holds mel bins 8 j .. 8 j + 7 (one per warp): mel_len10 bins are read, the weights are stored padded to a multiple
+// of four (aligned float4 loads)
+__host__ __device__ constexpr int mel_len10(int j) {
+    return j < 4 ? 2 : j < 6 ? 4 : j == 6 ? 6 : j == 7 ? 8 : j == 8 ? 11 : 14;
+}
+__host__ __device__ constexpr int mel_pad10(int j) { return (mel_len10(j) + 3) & ~3; }
+__host__ __device__ constexpr int mel_off10(int j) { return j == 0 ? 0 : mel_off10(j - 1) + 8 * mel_pad10(j - 1); }
+static_assert(mel_off10(10) <= kMelWeights, "the half-slot table fits the array of the slot table");
 
 __constant__ float  cw_win[16][25];     // [n2][n1] = hann[16 n1 + n2]
 __constant__ float2 cw_tw[16][16];      // [n2][k1] = W400^(n2 k1), k1 = 0..12
@@ -146,6 +160,24 @@ __device__ __forceinline__ float mel_slot(const float* __restrict__ Pl, const fl
         acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
         acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
         acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
+    }
+    return log10_pos(fmaxf(acc0 + acc1, 1e-10f));
+}
+
+template <int kHalfSlot>
+__device__ __forceinline__ float mel_slot10(const float* __restrict__ Pl, const float* __restrict__ melw,
+                                            const int* __restrict__ melfirst, int warp) {
+    constexpr int L = mel_len10(kHalfSlot), PAD = mel_pad10(kHalfSlot);
+    const float4* w4 = reinterpret_cast<const float4*>(melw + mel_off10(kHalfSlot) + warp * PAD);
+    const float* pk = Pl + melfirst[8 * kHalfSlot + warp] * kTile;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < PAD / 4; ++q) {
+        const float4 w = w4[q];
+        if (4 * q + 0 < L) acc0 = fmaf(w.x, pk[(4 * q + 0) * kTile], acc0);
+        if (4 * q + 1 < L) acc1 = fmaf(w.y, pk[(4 * q + 1) * kTile], acc1);
+        if (4 * q + 2 < L) acc0 = fmaf(w.z, pk[(4 * q + 2) * kTile], acc0);
+        if (4 * q + 3 < L) acc1 = fmaf(w.w, pk[(4 * q + 3) * kTile], acc1);
     }
     return log10_pos(fmaxf(acc0 + acc1, 1e-10f));
 }
@@ -342,6 +374,36 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
         {
             const float* Pl = &sm.u.P[0][lane];
             const int t = t0 + lane;
+#if STX_W_MEL_EXACT
+            // mel bin warp + 8 h + 16 i = bin `warp` of half slot 2 i + h
+            {
+                float v[5];
+                v[0] = mel_slot10<0>(Pl, sm.melw, sm.melfirst, warp);
+                v[1] = mel_slot10<2>(Pl, sm.melw, sm.melfirst, warp);
+                v[2] = mel_slot10<4>(Pl, sm.melw, sm.melfirst, warp);
+                v[3] = mel_slot10<6>(Pl, sm.melw, sm.melfirst, warp);
+                v[4] = mel_slot10<8>(Pl, sm.melw, sm.melfirst, warp);
+                if (t < t_end) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        out_b[(size_t)(warp + 16 * i) * T + t] = v[i];
+                        run_max = fmaxf(run_max, v[i]);
+                    }
+                }
+                v[0] = mel_slot10<1>(Pl, sm.melw, sm.melfirst, warp);
+                v[1] = mel_slot10<3>(Pl, sm.melw, sm.melfirst, warp);
+                v[2] = mel_slot10<5>(Pl, sm.melw, sm.melfirst, warp);
+                v[3] = mel_slot10<7>(Pl, sm.melw, sm.melfirst, warp);
+                v[4] = mel_slot10<9>(Pl, sm.melw, sm.melfirst, warp);
+                if (t < t_end) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        out_b[(size_t)(warp + 8 + 16 * i) * T + t] = v[i];
+                        run_max = fmaxf(run_max, v[i]);
+                    }
+                }
+            }
+#else
 #pragma unroll 1
             for (int role = warp; role < 16; role += kWarps) {
                 float v[5];
@@ -358,6 +420,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                     }
                 }
             }
+#endif
         }
         __syncthreads();                            // the power spectrum is consumed: the next layout pass may overwrite it
         }
@@ -425,6 +488,19 @@ int get_tables(const WTables** out) {
         STX_CUDA(cudaMemcpyToSymbol(cw_win, win, sizeof(win)));
         STX_CUDA(cudaMemcpyToSymbol(cw_tw, tw, sizeof(tw)));
         const std::vector<double>& fb = w_mel();
+#if STX_W_MEL_EXACT
+        for (int i = 0; i < kMelWeights; ++i) h.melw[i] = 0.0f;
+        for (int m = 0; m < kMel; ++m) {
+            const int j = m / 8, wrp = m % 8, L = mel_len10(j), PAD = mel_pad10(j);
+            int lo = -1, hi = -1;
+            for (int k = 0; k < kBins; ++k)
+                if (fb[size_t(k) * kMel + m] != 0.0) { if (lo < 0) lo = k; hi = k; }
+            if (lo < 0 || hi - lo + 1 > L) { set_error("mel filter %d does not fit its half slot", m); return STX_EINVAL; }
+            if (lo + L > kBins) lo = kBins - L;
+            h.melfirst[m] = lo;
+            for (int q = 0; q < L; ++q) h.melw[mel_off10(j) + wrp * PAD + q] = float(fb[size_t(lo + q) * kMel + m]);
+        }
+#else
         for (int m = 0; m < kMel; ++m) {
             const int slot = m / 16, wrp = m % 16, L = mel_len(slot);
             int lo = -1, hi = -1;
@@ -435,6 +511,7 @@ int get_tables(const WTables** out) {
             h.melfirst[m] = lo;
             for (int q = 0; q < L; ++q) h.melw[mel_off(slot) + wrp * L + q] = float(fb[size_t(lo + q) * kMel + m]);
         }
+#endif
         WTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(WTables)));
         STX_CUDA(cudaMemcpy(d, &h, sizeof(WTables), cudaMemcpyHostToDevice));
