@@ -56,6 +56,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 // Build-time switches for A/B runs (tools/ab_build.py); the defaults are the shipped configuration.
 #ifndef STX_K_MEL_GEN
@@ -131,6 +132,13 @@
                                  //    group) whose lengths are the longest filter of the half slot (2, 3, 3, 4, 5, 6, 8, 10, 13, 16
                                  //    bins: 560 bin reads and FMAs per frame) instead of five slots of 16 padded to 4, 4, 8, 12, 16
                                  //    (704): 206.4 -> 201.4 us on cfg2, bit-identical (the dropped products had zero weights)
+#endif
+#ifndef STX_K_H2_TMEM
+#define STX_K_H2_TMEM 0          // 1: the rows of the second exchange half that a warp needs from the two warps sharing its tensor-memory
+                                 //    lane quarter (4 of the 16 roles, itself included) are read straight from their stash
+                                 //    (tcgen05.ld) instead of going through shared memory: a quarter of the H2 stores and loads
+                                 //    (256 of ~5500 shared-memory wavefronts per tile).  Bit-identical and no faster (201.2 against
+                                 //    200.5 us on cfg2): the exchange phases are not bound by their wavefront count
 #endif
 #ifndef STX_K_SOLO
 #define STX_K_SOLO 0             // 1 (experiment): only group 0 of every CTA works
@@ -1113,12 +1121,21 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
             tmem_st16(tstash + (unsigned)(which * 32), hs);
 #endif
         };
+#if STX_K_H2_TMEM
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");     // the quarter mates have read the previous tile's stash
+#endif
         pass1(w8, 0);
         pass1(w8 + kGWarps, 1);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#if STX_K_H2_TMEM
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // the stash is read by the quarter mates behind this barrier
+#endif
         KTRACE_PRE(0);
         group_bar(g);                               // H1 complete, psum complete; d is dead, its storage becomes the power spectrum
         KTRACE(0);
+#if STX_K_H2_TMEM
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
 
         // ---- c = 0.03 * mean(frame): warp w8 sums the 16 partials of frames 4 w8 .. 4 w8 + 3 ----
         {
@@ -1149,11 +1166,20 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         {
             double hs[16];
             tmem_ld16(tstash, hs);
+#if STX_K_H2_TMEM
+            // rows 8 + s with s = w8 (mod 4) go to a warp of this lane quarter, which reads them from the stash itself
+#pragma unroll
+            for (int s = 0; s < 8; ++s) if ((s & 3) != (w8 & 3)) sg.ex[s][w8][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
+            tmem_ld16(tstash + 32u, hs);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) if ((s & 3) != (w8 & 3)) sg.ex[s][w8 + kGWarps][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
+#else
 #pragma unroll
             for (int s = 0; s < 8; ++s) sg.ex[s][w8][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
             tmem_ld16(tstash + 32u, hs);
 #pragma unroll
             for (int s = 0; s < 8; ++s) sg.ex[s][w8 + kGWarps][lane] = make_double2(hs[2 * s], hs[2 * s + 1]);
+#endif
         }
 #if !STX_K_BAR2_LATE
         KTRACE_PRE(2);
@@ -1197,12 +1223,50 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
         {
             const int row = kGWarps + w8;
             constexpr int kOrder2[16] = {0, 8, 4, 12, 1, 9, 5, 13, 2, 10, 6, 14, 3, 11, 7, 15};
+#if STX_K_H2_TMEM
+            // roles n2 = q, q + 4, q + 8, q + 12 (q = w8 mod 4) were produced by the two warps of this lane quarter (p = q and
+            // q + 4, first and second role each): row 8 + w8 = doubles 2 w8, 2 w8 + 1 of their stashes.  One code path per q,
+            // so that the register of every n2 is fixed
+            const unsigned tq = sm.tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(g * 128) + 4u * (unsigned)w8;
+            auto load_half = [&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                unsigned r[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                // role n2 = q + 4 i: producer warp n2 % 8 of the group, its role n2 / 8
+                    const int n2 = q + 4 * i;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(r[i][0]), "=r"(r[i][1]), "=r"(r[i][2]), "=r"(r[i][3])
+                                 : "r"(tq + (unsigned)(((n2 & 7) >> 2) * 64 + (n2 >> 3) * 32)) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n2 = kOrder2[j];
+                    if ((n2 & 3) == q) continue;
+                    const double2 v = lds_v2f64(&sg.ex[w8][n2][lane]);
+                    xr[n2] = v.x; xi[n2] = v.y;
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    xr[q + 4 * i] = __hiloint2double((int)r[i][1], (int)r[i][0]);
+                    xi[q + 4 * i] = __hiloint2double((int)r[i][3], (int)r[i][2]);
+                }
+            };
+            switch (w8 & 3) {
+                case 0: load_half(std::integral_constant<int, 0>()); break;
+                case 1: load_half(std::integral_constant<int, 1>()); break;
+                case 2: load_half(std::integral_constant<int, 2>()); break;
+                default: load_half(std::integral_constant<int, 3>()); break;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // (the next pass 1 of the quarter mates overwrites the stash)
+#else
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const int n2 = kOrder2[j];
                 const double2 v = lds_v2f64(&sg.ex[w8][n2][lane]);
                 xr[n2] = v.x; xi[n2] = v.y;
             }
+#endif
             double yr[16], yi[16];
             codelets::dft16<double>(xr, xi, yr, yi);
 #pragma unroll
