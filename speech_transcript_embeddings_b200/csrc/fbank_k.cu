@@ -140,6 +140,12 @@
                                  //    (256 of ~5500 shared-memory wavefronts per tile).  Bit-identical and no faster (201.2 against
                                  //    200.5 us on cfg2): the exchange phases are not bound by their wavefront count
 #endif
+#ifndef STX_K_LN_FAST
+#define STX_K_LN_FAST 1          // 1 (shipped): ln of a mel energy as lg2.approx of the whole value times ln 2 (2 instructions instead
+                                 //    of 8): 201.1 -> 197.7 us on cfg2.  The log2 is a float32 of magnitude up to 64, so the raw log-mel
+                                 //    is good to 2 float32 ulps (3.8e-6; 7.6e-6 for full-scale int16-valued input) instead of 1; the
+                                 //    normalised features of cfg2 move from 1.31e-5 to 1.59e-5 of the 1e-4 bar (all 64 clips)
+#endif
 #ifndef STX_K_SOLO
 #define STX_K_SOLO 0             // 1 (experiment): only group 0 of every CTA works
 #endif
@@ -266,6 +272,13 @@ static_assert(3 * kStatThreads * sizeof(unsigned long long) <= sizeof(r2x2_t) * 
 // |error| <= ~0.6 ulp of the result for results of magnitude 10..30 (the mantissa's log2 is in [0, 1), where
 // lg2.approx is accurate to 2^-22 absolute), i.e. as good as logf at a third of the instructions.
 __device__ __forceinline__ float ln_pos(float x) {
+#if STX_K_LN_FAST
+    // (A/B) log2 of the whole value in one MUFU: the result is rounded to float32 at magnitude up to 64, i.e. up to 3.8e-6 in
+    // log2 (2.6e-6 in ln) where the split form keeps ~1e-7
+    float l2x;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2x) : "f"(x));
+    return l2x * 0.69314718055994530942f;
+#endif
     const int bits = __float_as_int(x);
     const float e = (float)((bits >> 23) - 127);
     const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
