@@ -146,6 +146,12 @@
                                  //    is good to 2 float32 ulps (3.8e-6; 7.6e-6 for full-scale int16-valued input) instead of 1; the
                                  //    normalised features of cfg2 move from 1.31e-5 to 1.59e-5 of the 1e-4 bar (all 64 clips)
 #endif
+#ifndef STX_K_STATS_TILE
+#define STX_K_STATS_TILE 1       // 1 (shipped, 197.8 -> 196.4 us on cfg2): a thread sums its <= 11 values of a tile (and their squares) in float64 first and converts the two
+                                 //    sums to fixed point once per tile, instead of converting every value (5 FP64 + 6 integer
+                                 //    instructions per value become 2 FP64).  The tile grid of a clip does not depend on the batch, so
+                                 //    the statistics stay batch-invariant; they differ from the per-value form in the last bits
+#endif
 #ifndef STX_K_SOLO
 #define STX_K_SOLO 0             // 1 (experiment): only group 0 of every CTA works
 #endif
@@ -1377,6 +1383,22 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
 #pragma unroll
                 for (int i = 0; i < 10; ++i) dst[i * kGStat] = v[i];
                 if (srow < 2) dst[10 * kGStat] = v[10];
+#if STX_K_STATS_TILE
+                double a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const double vd = (double)v[i];
+                    a1[i & 1] += vd;
+                    a2[i & 1] = fma(vd, vd, a2[i & 1]);
+                }
+                {
+                    const double t1 = a1[0] + a1[1], t2 = a2[0] + a2[1];
+                    const double hi = t2 + kFixH, lo = t2 - (hi - kFixH);
+                    s1 += (unsigned long long)__double_as_longlong(t1 + kFix1) - (unsigned long long)__double_as_longlong(kFix1);
+                    s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
+                    s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < 11; ++i) {
                     const double vd = (double)v[i];
@@ -1385,8 +1407,31 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                     s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
                     s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
                 }
+#endif
             } else
 #endif
+#if STX_K_STATS_TILE
+            {
+                // (partial tile: the same two accumulators per parity of i as the full-tile path, rows past the end add nothing)
+                double a1[2] = {0.0, 0.0}, a2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const int row = srow + 3 * i;
+                    if (row < rows) {
+                        const float v = outstage[row * kOutRow + sbin];
+                        if (row < keep) dst[i * kGStat] = v;
+                        const double vd = (double)v;
+                        a1[i & 1] += vd;
+                        a2[i & 1] = fma(vd, vd, a2[i & 1]);
+                    }
+                }
+                const double t1 = a1[0] + a1[1], t2 = a2[0] + a2[1];
+                const double hi = t2 + kFixH, lo = t2 - (hi - kFixH);
+                s1 += (unsigned long long)__double_as_longlong(t1 + kFix1) - (unsigned long long)__double_as_longlong(kFix1);
+                s2h += (unsigned long long)__double_as_longlong(hi) - (unsigned long long)__double_as_longlong(kFixH);
+                s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
+            }
+#else
 #pragma unroll
             for (int i = 0; i < 11; ++i) {
                 const int row = srow + 3 * i;
@@ -1400,6 +1445,7 @@ k_frames_duo(const float* __restrict__ pcm, const long long* __restrict__ offset
                     s2l += (unsigned long long)__double_as_longlong(lo + kFixL) - (unsigned long long)__double_as_longlong(kFixL);
                 }
             }
+#endif
         }
         if (cur.last) {
             // ---- last tile of the item: the group's 3 row groups -> partials[item] (ordered, integer: exact) ----
