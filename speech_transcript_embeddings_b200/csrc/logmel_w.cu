@@ -49,6 +49,7 @@ constexpr int kXBuf = 34 * kXRow;
 __host__ __device__ constexpr int mel_len(int slot) { return slot < 3 ? 4 : slot == 3 ? 8 : 16; }
 __host__ __device__ constexpr int mel_off(int slot) { return slot == 0 ? 0 : mel_off(slot - 1) + 16 * mel_len(slot - 1); }
 constexpr int kMelWeights = mel_off(5);  // 576
+constexpr int kStockSamples = 480000;   // the recipe's stock chunk: 30 s (w_frames is specialised for it)
 #ifndef STX_W_MEL_EXACT
 #define STX_W_MEL_EXACT 1               // 1 (shipped): the mel stage walks ten half slots of 8 filters (one per warp) whose lengths are
                                         //    the longest filter of the half slot (2, 2, 2, 2, 4, 4, 6, 8, 11, 14 bins: 440 bin reads and
@@ -209,13 +210,18 @@ __device__ __forceinline__ float max_unkey(unsigned k) {
 // Launch bound of THREE CTAs per SM although shared memory admits two: at the 80 registers that bound implies ptxas reads the
 // per-role window / twiddle tables through the uniform datapath (84 LDCU, no spills); at 126 registers it reads them with
 // register-indexed LDCs, which queue in the MIO behind the shared-memory traffic (the two hottest lines of the round-1 kernel).
+// kFixedSamples: n_samples at compile time (the stock 30 s chunk: 480 000), 0 = taken from the argument.  With T = n_samples / 160
+// a constant, the ten output rows of a warp ([B, 80, T]: rows are T floats apart) are immediate offsets from one pointer
+// instead of a 64-bit multiply-add and a two-instruction address per store (40 of ~330 instructions of the mel stage).
+template <int kFixedSamples>
 __global__ void __launch_bounds__(kThreads, 3)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
-         const float* __restrict__ peaks, const WTables* __restrict__ tab, int B, int n_samples, int chunk_frames,
+         const float* __restrict__ peaks, const WTables* __restrict__ tab, int B, int n_samples_arg, int chunk_frames,
          int chunks_per_clip, float* __restrict__ out, unsigned* __restrict__ clip_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
+    const int n_samples = kFixedSamples ? kFixedSamples : n_samples_arg;
     const int T = n_samples / kHop;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -393,10 +399,11 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 v[2] = mel_slot10<4>(Pl, sm.melw, sm.melfirst, warp);
                 v[3] = mel_slot10<6>(Pl, sm.melw, sm.melfirst, warp);
                 v[4] = mel_slot10<8>(Pl, sm.melw, sm.melfirst, warp);
+                float* const po = out_b + (size_t)warp * T + t;      // mel bin `warp`, frame t; bin m is m * T floats further
                 if (t < t_end) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
-                        out_b[(size_t)(warp + 16 * i) * T + t] = v[i];
+                        po[(size_t)(16 * i) * T] = v[i];
                         run_max = fmaxf(run_max, v[i]);
                     }
                 }
@@ -408,7 +415,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 if (t < t_end) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
-                        out_b[(size_t)(warp + 8 + 16 * i) * T + t] = v[i];
+                        po[(size_t)(8 + 16 * i) * T] = v[i];
                         run_max = fmaxf(run_max, v[i]);
                     }
                 }
@@ -525,8 +532,10 @@ int get_tables(const WTables** out) {
         WTables* d = nullptr;
         STX_CUDA(cudaMalloc(&d, sizeof(WTables)));
         STX_CUDA(cudaMemcpy(d, &h, sizeof(WTables), cudaMemcpyHostToDevice));
-        STX_CUDA(cudaFuncSetAttribute(w_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-        STX_CUDA(cudaFuncSetAttribute(w_frames, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        STX_CUDA(cudaFuncSetAttribute(w_frames<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        STX_CUDA(cudaFuncSetAttribute(w_frames<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        STX_CUDA(cudaFuncSetAttribute(w_frames<kStockSamples>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        STX_CUDA(cudaFuncSetAttribute(w_frames<kStockSamples>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         g_tab[dev] = d;
     }
     *out = g_tab[dev];
@@ -590,9 +599,14 @@ int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_
     }
     const int chunks = (T + chunk_frames - 1) / chunk_frames;
     const int grid = (int)std::min<long long>(2LL * sms, (long long)B * chunks);
-    STX_LAUNCH(w_frames, dim3(grid), dim3(kThreads), sizeof(Smem), st,
-               d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, n_samples, chunk_frames,
-               chunks, d_out, clip_max);
+    if (n_samples == kStockSamples)
+        STX_LAUNCH(w_frames<kStockSamples>, dim3(grid), dim3(kThreads), sizeof(Smem), st,
+                   d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, n_samples, chunk_frames,
+                   chunks, d_out, clip_max);
+    else
+        STX_LAUNCH(w_frames<0>, dim3(grid), dim3(kThreads), sizeof(Smem), st,
+                   d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, n_samples, chunk_frames,
+                   chunks, d_out, clip_max);
     const size_t total = (size_t)kMel * T;
     const int gx = (int)std::max<size_t>(1, std::min<size_t>((total / 4 + 255) / 256, 64));
     STX_LAUNCH(w_finish, dim3(gx, B), dim3(256), 0, st, d_lengths, clip_max, n_samples, d_out, d_mask);
