@@ -707,8 +707,8 @@ class _QuietStdout:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--recipe", choices=["K", "W"], default="K")
     ap.add_argument("--no-cpu-baseline", action="store_true")
