@@ -3,6 +3,8 @@
 //   A  one 123 MB pinned buffer, non-temporal stores, chunk by chunk, cudaMemcpyAsync per chunk (what the library does)
 //   B  ring of R pinned slots of one chunk each, REGULAR stores; a slot is reused once its H2D copy has completed
 //   C  ring, non-temporal stores
+//   D  one 123 MB WRITE-COMBINED pinned buffer (cudaHostAllocWriteCombined: not snooped by PCIe reads), non-temporal stores
+//   E  the H2D copies alone (buffer already packed)        F  the packing alone (no copies)
 // 64 pageable source buffers of 30 s (1.92 MB each), T packing threads, 62 MB of D2H traffic in flight on another stream.
 // Build: nvcc -O3 -std=c++17 -o tools/microbench_staging tools/microbench_staging.cu -Xcompiler -mavx2,-pthread
 #include <cuda_runtime.h>
@@ -46,7 +48,8 @@ int main(int argc, char** argv) {
     const int R = argc > 3 ? atoi(argv[3]) : 4;
     std::vector<unsigned char*> src(B);
     for (auto& p : src) { p = (unsigned char*)malloc(clip); memset(p, 1, clip); }
-    unsigned char *big, *ring, *hout, *dpcm, *dout;
+    unsigned char *big, *bigwc, *ring, *hout, *dpcm, *dout;
+    CHECK(cudaHostAlloc(&bigwc, total, cudaHostAllocWriteCombined));
     CHECK(cudaMallocHost(&big, total)); CHECK(cudaMallocHost(&ring, chunk * R)); CHECK(cudaMallocHost(&hout, total / 2));
     CHECK(cudaMalloc(&dpcm, total)); CHECK(cudaMalloc(&dout, total / 2));
     memset(big, 0, total); memset(ring, 0, chunk * R); memset(hout, 0, total / 2);
@@ -72,9 +75,10 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 8; ++i) CHECK(cudaMemcpyAsync(hout + i * (total / 16), dout + i * (total / 16), total / 16, cudaMemcpyDeviceToHost, s_out));
         for (int c = 0; c < nchunks; ++c) {
             const size_t lo = c * chunk, hi = std::min(total, lo + chunk);
-            if (mode == 0) {
-                pack_chunk(big + lo, lo, hi, true);
-                CHECK(cudaMemcpyAsync(dpcm + lo, big + lo, hi - lo, cudaMemcpyHostToDevice, s_in));
+            if (mode == 0 || mode >= 3) {
+                unsigned char* buf = mode == 3 ? bigwc : big;
+                if (mode != 4) pack_chunk(buf + lo, lo, hi, true);
+                if (mode != 5) CHECK(cudaMemcpyAsync(dpcm + lo, buf + lo, hi - lo, cudaMemcpyHostToDevice, s_in));
             } else {
                 if (c >= R) CHECK(cudaEventSynchronize(ev[c - R]));
                 unsigned char* slot = ring + (c % R) * chunk;
@@ -85,10 +89,11 @@ int main(int argc, char** argv) {
         }
         CHECK(cudaStreamSynchronize(s_in)); CHECK(cudaStreamSynchronize(s_out));
     };
-    const char* names[3] = {"A  one big buffer, non-temporal stores", "B  ring, regular stores", "C  ring, non-temporal stores"};
+    const char* names[6] = {"A  one big buffer, non-temporal stores", "B  ring, regular stores", "C  ring, non-temporal stores",
+                            "D  one big WRITE-COMBINED buffer, NT stores", "E  H2D copies alone", "F  packing alone"};
     printf("%d threads, chunk %.1f MB, ring of %d slots (%.1f MB)\n", T, chunk / 1e6, R, chunk * R / 1e6);
     for (int rep = 0; rep < 2; ++rep)
-        for (int mode = 0; mode < 3; ++mode) {
+        for (int mode = 0; mode < 6; ++mode) {
             run(mode); run(mode);
             const auto t0 = std::chrono::steady_clock::now();
             const int iters = 10;
