@@ -76,6 +76,7 @@ struct WTables {
 // One 32-frame tile of a work item (clip b, chunk of frames), kept in shared memory and read where it is used
 struct WTile {
     const float* clip; float* out_b; unsigned* cmax;
+    float* fmin_b;                      // (STX_W_LAZY_CLAMP) [8 warps][T]: smallest log10 of the warp's ten mel bins per frame
     int len, t0, t_end, item;
     float peak;
     int aligned, valid, last;           // last: the item ends with this tile (publish the running maximum)
@@ -135,6 +136,15 @@ __device__ __forceinline__ StageRange stage_range(int g0, int len, bool aligned)
 // log10(x) for normal positive x (the 1e-10 floor guarantees it): exponent + MUFU.LG2 of the mantissa, times log10(2).
 // The mantissa's log2 is in [0, 1), where lg2.approx is accurate to 2^-22 absolute, so the result is within 1e-7 of
 // log10f at a third of its instructions (the bar on log10 is 4e-4).
+#ifndef STX_W_LAZY_CLAMP
+#define STX_W_LAZY_CLAMP 1              // 1 (shipped): w_frames writes the final (x + 4) / 4 itself and leaves, per frame and warp, the
+                                        //    smallest log10 it produced; w_finish then touches only the frames that the per-clip clamp
+                                        //    max(x, max - 8) actually changes (max commutes with the monotone (x + 4) / 4, so the bits are
+                                        //    those of clamp-then-scale).  For audio without 8 decades of dynamic range inside a clip --
+                                        //    anything but digital silence and zero padding -- the second pass over the 61 MB of cfg2
+                                        //    becomes a 6 MB read.  0: w_finish rewrites every value (rounds 1 and 2)
+#endif
+static_assert(!STX_W_LAZY_CLAMP || STX_W_MEL_EXACT, "the lazy clamp is written into the half-slot mel stage");
 #ifndef STX_W_LOG_FAST
 #define STX_W_LOG_FAST 1                // 1 (shipped): log10 of a mel energy as lg2.approx of the whole value times log10(2): 2 instructions
                                         //    instead of 8.  The result is a float32 of magnitude up to 33 in log2, i.e. good to 3.8e-6 there,
@@ -217,7 +227,7 @@ template <int kFixedSamples>
 __global__ void __launch_bounds__(kThreads, 3)
 w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, const int* __restrict__ lengths,
          const float* __restrict__ peaks, const WTables* __restrict__ tab, int B, int n_samples_arg, int chunk_frames,
-         int chunks_per_clip, float* __restrict__ out, unsigned* __restrict__ clip_max) {
+         int chunks_per_clip, float* __restrict__ out, unsigned* __restrict__ clip_max, float* __restrict__ frame_min) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -240,6 +250,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             d.peak = peaks ? __ldg(peaks + b) : 1.0f;
             d.out_b = out + (size_t)b * kMel * T;
             d.cmax = clip_max + b;
+            d.fmin_b = frame_min + (size_t)b * kWarps * T;
         }
     };
     auto next_tile = [&](WTile& c, WTile& d) {       // (thread 0 only) d = the tile after c
@@ -285,8 +296,14 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             const float v = log10_pos(1e-10f);
             const int t = t0 + lane;
             if (t < t_end) {
+#if STX_W_LAZY_CLAMP
+#pragma unroll
+                for (int i = 0; i < 10; ++i) out_b[(size_t)(warp + 8 * i) * T + t] = fmaf(v, 0.25f, 1.0f);
+                cur.fmin_b[(size_t)warp * T + t] = v;
+#else
 #pragma unroll
                 for (int i = 0; i < 10; ++i) out_b[(size_t)(warp + 8 * i) * T + t] = v;
+#endif
                 run_max = fmaxf(run_max, v);
             }
             __syncthreads();                        // every warp is done with the previous tile's descriptor (the other slot)
@@ -400,6 +417,16 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                 v[3] = mel_slot10<6>(Pl, sm.melw, sm.melfirst, warp);
                 v[4] = mel_slot10<8>(Pl, sm.melw, sm.melfirst, warp);
                 float* const po = out_b + (size_t)warp * T + t;      // mel bin `warp`, frame t; bin m is m * T floats further
+#if STX_W_LAZY_CLAMP
+                float lo5 = fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), v[4]);
+                if (t < t_end) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        po[(size_t)(16 * i) * T] = fmaf(v[i], 0.25f, 1.0f);      // = (x + 4) / 4 in float32, bit for bit
+                        run_max = fmaxf(run_max, v[i]);
+                    }
+                }
+#else
                 if (t < t_end) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
@@ -407,11 +434,23 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                         run_max = fmaxf(run_max, v[i]);
                     }
                 }
+#endif
                 v[0] = mel_slot10<1>(Pl, sm.melw, sm.melfirst, warp);
                 v[1] = mel_slot10<3>(Pl, sm.melw, sm.melfirst, warp);
                 v[2] = mel_slot10<5>(Pl, sm.melw, sm.melfirst, warp);
                 v[3] = mel_slot10<7>(Pl, sm.melw, sm.melfirst, warp);
                 v[4] = mel_slot10<9>(Pl, sm.melw, sm.melfirst, warp);
+#if STX_W_LAZY_CLAMP
+                lo5 = fminf(lo5, fminf(fminf(fminf(v[0], v[1]), fminf(v[2], v[3])), v[4]));
+                if (t < t_end) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        po[(size_t)(8 + 16 * i) * T] = fmaf(v[i], 0.25f, 1.0f);
+                        run_max = fmaxf(run_max, v[i]);
+                    }
+                    cur.fmin_b[(size_t)warp * T + t] = lo5;
+                }
+#else
                 if (t < t_end) {
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
@@ -419,6 +458,7 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
                         run_max = fmaxf(run_max, v[i]);
                     }
                 }
+#endif
             }
 #else
 #pragma unroll 1
@@ -454,12 +494,51 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
 // max(x, max - 8), (x + 4) / 4 in place; mask[b, j] = (160 j < len)
 __global__ void __launch_bounds__(256)
 w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max, int n_samples,
-         float* __restrict__ out, int* __restrict__ mask) {
+         float* __restrict__ out, int* __restrict__ mask, const float* __restrict__ frame_min) {
     const int b = blockIdx.y;
     const int T = n_samples / kHop;
     const float lo = max_unkey(clip_max[b]) - 8.0f;
     const size_t total = (size_t)kMel * T;
     float* o = out + (size_t)b * total;
+#if STX_W_LAZY_CLAMP
+    // one thread per frame: the frame's smallest log10 (over the eight warps' minima) against the clip's floor; a frame below it
+    // is clamped in place in the scaled domain.  (x + 4) / 4 is monotone, so max((x + 4) / 4, (lo + 4) / 4) has the bits of
+    // (max(x, lo) + 4) / 4
+    {
+        const float* fm = frame_min + (size_t)b * kWarps * T;
+        const float ylo = fmaf(lo, 0.25f, 1.0f);
+        auto clamp_frame = [&](int t) {
+#pragma unroll 8
+            for (int r = 0; r < kMel; ++r) o[(size_t)r * T + t] = fmaxf(o[(size_t)r * T + t], ylo);
+        };
+        if ((T & 3) == 0 && (reinterpret_cast<unsigned long long>(fm) & 15ull) == 0) {
+            // four frames per thread: eight 16-byte loads
+            const float4* fm4 = reinterpret_cast<const float4*>(fm);
+            const int T4 = T >> 2;
+            for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < T4; q += gridDim.x * blockDim.x) {
+                float4 m = fm4[q];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) {
+                    const float4 v = fm4[(size_t)w * T4 + q];
+                    m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z); m.w = fminf(m.w, v.w);
+                }
+                if (fminf(fminf(m.x, m.y), fminf(m.z, m.w)) < lo) {
+                    if (m.x < lo) clamp_frame(4 * q);
+                    if (m.y < lo) clamp_frame(4 * q + 1);
+                    if (m.z < lo) clamp_frame(4 * q + 2);
+                    if (m.w < lo) clamp_frame(4 * q + 3);
+                }
+            }
+        } else {
+            for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+                float m = fm[t];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) m = fminf(m, fm[(size_t)w * T + t]);
+                if (m < lo) clamp_frame(t);
+            }
+        }
+    }
+#else
     const bool vec = (total % 4 == 0);
     if (vec) {
         float4* o4 = reinterpret_cast<float4*>(o);
@@ -475,6 +554,7 @@ w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max,
         for (size_t q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x)
             o[q] = (fmaxf(o[q], lo) + 4.0f) / 4.0f;
     }
+#endif
     if (mask) {
         const int len = min(lengths[b], n_samples);
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < T; j += gridDim.x * blockDim.x)
@@ -561,8 +641,9 @@ extern "C" {
 
 int stx_logmel_w_workspace(int B, int n_samples, size_t* bytes) {
     if (B < 0 || n_samples < 0 || !bytes) { stx::set_error("stx_logmel_w_workspace: bad argument"); return STX_EINVAL; }
-    *bytes = (size_t(B) * sizeof(float) + 255) & ~size_t(255);
-    if (*bytes == 0) *bytes = 256;
+    // the per-clip maxima, then (STX_W_LAZY_CLAMP) the per-frame, per-warp minima [B][8][n_samples / 160]
+    *bytes = ((size_t(B) * sizeof(float) + 255) & ~size_t(255)) + 256 +
+             ((size_t(B) * stx::kWarps * (size_t)(n_samples / stx::kHop) * sizeof(float) + 255) & ~size_t(255));
     return 0;
 }
 
@@ -584,6 +665,7 @@ int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_
     if (int rc = get_tables(&tab)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned* clip_max = static_cast<unsigned*>(d_ws);
+    float* frame_min = reinterpret_cast<float*>(static_cast<unsigned char*>(d_ws) + ((size_t(B) * sizeof(float) + 255) & ~size_t(255)) + 256);
     const int T = n_samples / kHop;
     STX_CUDA(cudaMemsetAsync(clip_max, 0, size_t(B) * sizeof(unsigned), st));
     static int sms = 0;
@@ -602,14 +684,18 @@ int stx_logmel_w(const float* d_pcm, const int64_t* d_offsets, const int32_t* d_
     if (n_samples == kStockSamples)
         STX_LAUNCH(w_frames<kStockSamples>, dim3(grid), dim3(kThreads), sizeof(Smem), st,
                    d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, n_samples, chunk_frames,
-                   chunks, d_out, clip_max);
+                   chunks, d_out, clip_max, frame_min);
     else
         STX_LAUNCH(w_frames<0>, dim3(grid), dim3(kThreads), sizeof(Smem), st,
                    d_pcm, reinterpret_cast<const long long*>(d_offsets), d_lengths, d_peak, tab, B, n_samples, chunk_frames,
-                   chunks, d_out, clip_max);
+                   chunks, d_out, clip_max, frame_min);
+#if STX_W_LAZY_CLAMP
+    const int gx = std::max(1, ((T + 3) / 4 + 255) / 256);  // one thread per four frames
+#else
     const size_t total = (size_t)kMel * T;
     const int gx = (int)std::max<size_t>(1, std::min<size_t>((total / 4 + 255) / 256, 64));
-    STX_LAUNCH(w_finish, dim3(gx, B), dim3(256), 0, st, d_lengths, clip_max, n_samples, d_out, d_mask);
+#endif
+    STX_LAUNCH(w_finish, dim3(gx, B), dim3(256), 0, st, d_lengths, clip_max, n_samples, d_out, d_mask, (const float*)frame_min);
     return 0;
 }
 
