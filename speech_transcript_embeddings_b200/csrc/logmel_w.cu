@@ -511,7 +511,7 @@ w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max,
 #pragma unroll 8
             for (int r = 0; r < kMel; ++r) o[(size_t)r * T + t] = fmaxf(o[(size_t)r * T + t], ylo);
         };
-        if ((T & 3) == 0 && (reinterpret_cast<unsigned long long>(fm) & 15ull) == 0) {
+        if ((T & 3) == 0 && ((reinterpret_cast<unsigned long long>(fm) | reinterpret_cast<unsigned long long>(o)) & 15ull) == 0) {
             // four frames per thread: eight 16-byte loads
             const float4* fm4 = reinterpret_cast<const float4*>(fm);
             const int T4 = T >> 2;
@@ -523,10 +523,15 @@ w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max,
                     m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z); m.w = fminf(m.w, v.w);
                 }
                 if (fminf(fminf(m.x, m.y), fminf(m.z, m.w)) < lo) {
-                    if (m.x < lo) clamp_frame(4 * q);
-                    if (m.y < lo) clamp_frame(4 * q + 1);
-                    if (m.z < lo) clamp_frame(4 * q + 2);
-                    if (m.w < lo) clamp_frame(4 * q + 3);
+                    // (a frame whose minimum is not below the floor has every value at or above ylo: the max leaves it as it is,
+                    // so the four frames go through it together -- 16-byte accesses, consecutive threads on consecutive quads)
+                    float4* o4 = reinterpret_cast<float4*>(o) + q;
+#pragma unroll 8
+                    for (int r = 0; r < kMel; ++r) {
+                        float4 v = o4[(size_t)r * T4];
+                        v.x = fmaxf(v.x, ylo); v.y = fmaxf(v.y, ylo); v.z = fmaxf(v.z, ylo); v.w = fmaxf(v.w, ylo);
+                        o4[(size_t)r * T4] = v;
+                    }
                 }
             }
         } else {
