@@ -297,9 +297,10 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             const int t = t0 + lane;
             if (t < t_end) {
 #if STX_W_LAZY_CLAMP
-#pragma unroll
-                for (int i = 0; i < 10; ++i) out_b[(size_t)(warp + 8 * i) * T + t] = fmaf(v, 0.25f, 1.0f);
-                cur.fmin_b[(size_t)warp * T + t] = v;
+                // nothing is written for the frame: the minimum of warp 0 carries a marker (-inf) and w_finish, which knows the
+                // clip's floor by then, stores the final value of all 80 bins once (instead of a store here and a read-modify-write
+                // there: the zero padding of a short clip is always below the floor unless the whole clip is silent)
+                cur.fmin_b[(size_t)warp * T + t] = warp == 0 ? __int_as_float(0xff800000) : v;
 #else
 #pragma unroll
                 for (int i = 0; i < 10; ++i) out_b[(size_t)(warp + 8 * i) * T + t] = v;
@@ -507,29 +508,35 @@ w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max,
     {
         const float* fm = frame_min + (size_t)b * kWarps * T;
         const float ylo = fmaf(lo, 0.25f, 1.0f);
-        auto clamp_frame = [&](int t) {
-#pragma unroll 8
-            for (int r = 0; r < kMel; ++r) o[(size_t)r * T + t] = fmaxf(o[(size_t)r * T + t], ylo);
-        };
+        const float kNegInf = __int_as_float(0xff800000);
+        // a frame of a padding-only tile (marker -inf in warp 0's minimum) was not written at all: every bin is log10 of the
+        // 1e-10 floor there, so its final value is the same for all 80 bins
+        const float ypad = fmaf(fmaxf(log10_pos(1e-10f), lo), 0.25f, 1.0f);
         if ((T & 3) == 0 && ((reinterpret_cast<unsigned long long>(fm) | reinterpret_cast<unsigned long long>(o)) & 15ull) == 0) {
             // four frames per thread: eight 16-byte loads
             const float4* fm4 = reinterpret_cast<const float4*>(fm);
             const int T4 = T >> 2;
             for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < T4; q += gridDim.x * blockDim.x) {
                 float4 m = fm4[q];
+                const bool px = m.x == kNegInf, py = m.y == kNegInf, pz = m.z == kNegInf, pw = m.w == kNegInf;
 #pragma unroll
                 for (int w = 1; w < kWarps; ++w) {
                     const float4 v = fm4[(size_t)w * T4 + q];
                     m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z); m.w = fminf(m.w, v.w);
                 }
-                if (fminf(fminf(m.x, m.y), fminf(m.z, m.w)) < lo) {
+                float4* o4 = reinterpret_cast<float4*>(o) + q;
+                if (px && py && pz && pw) {
+                    const float4 v = make_float4(ypad, ypad, ypad, ypad);
+#pragma unroll 8
+                    for (int r = 0; r < kMel; ++r) o4[(size_t)r * T4] = v;
+                } else if (fminf(fminf(m.x, m.y), fminf(m.z, m.w)) < lo) {
                     // (a frame whose minimum is not below the floor has every value at or above ylo: the max leaves it as it is,
                     // so the four frames go through it together -- 16-byte accesses, consecutive threads on consecutive quads)
-                    float4* o4 = reinterpret_cast<float4*>(o) + q;
 #pragma unroll 8
                     for (int r = 0; r < kMel; ++r) {
                         float4 v = o4[(size_t)r * T4];
-                        v.x = fmaxf(v.x, ylo); v.y = fmaxf(v.y, ylo); v.z = fmaxf(v.z, ylo); v.w = fmaxf(v.w, ylo);
+                        v.x = px ? ypad : fmaxf(v.x, ylo); v.y = py ? ypad : fmaxf(v.y, ylo);
+                        v.z = pz ? ypad : fmaxf(v.z, ylo); v.w = pw ? ypad : fmaxf(v.w, ylo);
                         o4[(size_t)r * T4] = v;
                     }
                 }
@@ -537,9 +544,16 @@ w_finish(const int* __restrict__ lengths, const unsigned* __restrict__ clip_max,
         } else {
             for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
                 float m = fm[t];
+                const bool pad = m == kNegInf;
 #pragma unroll
                 for (int w = 1; w < kWarps; ++w) m = fminf(m, fm[(size_t)w * T + t]);
-                if (m < lo) clamp_frame(t);
+                if (pad) {
+#pragma unroll 8
+                    for (int r = 0; r < kMel; ++r) o[(size_t)r * T + t] = ypad;
+                } else if (m < lo) {
+#pragma unroll 8
+                    for (int r = 0; r < kMel; ++r) o[(size_t)r * T + t] = fmaxf(o[(size_t)r * T + t], ylo);
+                }
             }
         }
     }
