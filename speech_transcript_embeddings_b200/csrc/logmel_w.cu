@@ -65,7 +65,7 @@ __host__ __device__ constexpr int mel_pad10(int j) { return (mel_len10(j) + 3) &
 __host__ __device__ constexpr int mel_off10(int j) { return j == 0 ? 0 : mel_off10(j - 1) + 8 * mel_pad10(j - 1); }
 static_assert(mel_off10(10) <= kMelWeights, "the half-slot table fits the array of the slot table");
 
-__constant__ float  cw_win[16][25];     // [n2][n1] = hann[16 n1 + n2]
+__constant__ __align__(8) float cw_win[16][26];     // [n2][n1] = hann[16 n1 + n2]; rows padded to 26: read as 13 aligned pairs (LDCU.64)
 __constant__ float2 cw_tw[16][16];      // [n2][k1] = W400^(n2 k1), k1 = 0..12
 
 struct WTables {
@@ -357,7 +357,11 @@ w_frames(const float* __restrict__ pcm, const long long* __restrict__ offsets, c
             const float* X = sm.u.xs + kXRow * lane + role;
             float y[25], re[13], im[13];
 #pragma unroll
-            for (int n1 = 0; n1 < 25; ++n1) y[n1] = cw_win[role][n1] * X[16 * n1 + (n1 >= 10) + (n1 >= 20)];
+            for (int n1 = 0; n1 < 25; n1 += 2) {       // (window values in pairs: half the uniform loads)
+                const float2 wv = *reinterpret_cast<const float2*>(&cw_win[role][n1]);
+                y[n1] = wv.x * X[16 * n1 + (n1 >= 10) + (n1 >= 20)];
+                if (n1 + 1 < 25) y[n1 + 1] = wv.y * X[16 * (n1 + 1) + (n1 + 1 >= 10) + (n1 + 1 >= 20)];
+            }
             codelets::w_pass1<float>(y, re, im);
             sm.ex0[role][lane] = re[0];
 #pragma unroll
@@ -592,7 +596,7 @@ int get_tables(const WTables** out) {
     if (!g_tab[dev]) {
         static WTables h;
         const std::vector<double>& w = w_window();
-        static float win[16][25];
+        static float win[16][26] = {};
         static float2 tw[16][16];
         for (int n2 = 0; n2 < 16; ++n2)
             for (int n1 = 0; n1 < 25; ++n1) win[n2][n1] = (float)w[16 * n1 + n2];
